@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched IVP solves (forward BDF + adjoint gradient) per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lv_adj] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of synthetic parameter draws: for the default
+workload ``lv_adj`` (BASELINE.json configs[2], the configuration the metric "fwd+adjoint
+solves/s" is quoted on) that is 65 536 Lotka-Volterra forward+adjoint solves at rtol=atol=1e-8
+per GPU.  Multi-GPU runs (launched by torchrun, one rank per GPU) are weak-scaling: every rank
+solves its own 65 536 draws; the only collective is the all-gather of the outputs.
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'ivp_solves_per_sec_fwd_adjoint'
+L2_FLUSH_BYTES = 512 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='lv_adj')
+    ap.add_argument('--batch', type=int, default=None, help='instances per GPU (default: the workload\'s)')
+    ap.add_argument('--block', type=int, default=None)
+    ap.add_argument('--min-blocks', type=int, default=None)
+    ap.add_argument('--no-gather', action='store_true', help='skip the output all-gather at N > 1')
+    ap.add_argument('--cpu-sample', type=int, default=None, help='instances in the CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_solve(n_s, n_all, n_deriv, n_t, adjoint, mean_fwd_steps):
+    """I/O of one solve plus, for the adjoint, every accepted forward step's
+    (t, order, y) written once and read once."""
+    b = 8 * (n_s + n_all) + 8 * n_t * n_s
+    if adjoint:
+        b += 8 * n_t * n_s + 8 * (n_deriv + n_s) + 2 * 8 * mean_fwd_steps * (n_s + 2)
+    return float(b)
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as err:  # noqa: BLE001
+            self.err = repr(err)
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+            'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4),
+            'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+            'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+            'hw_power_brake_slowdown': getattr(nv, 'nvmlClocksEventReasonHwPowerBrakeSlowdown', 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as err:  # noqa: BLE001
+                self.err = repr(err)
+                break
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        out = {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+               'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+               'samples': len(self.samples)}
+        if self.err:
+            out['error'] = self.err
+        return out
+
+
+def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
+    """The oracle (CPU restatement of the reference path) on the host cores, bounded sample."""
+    from oracle.oracle import Oracle, max_threads
+    orc = Oracle(problem, rtol=1e-8, atol=1e-8)
+    y0, theta = w.draws(n_sample)
+    grads = np.ones((len(w.tvals), problem.n_states))
+    cores = threads or max_threads()
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        if adjoint:
+            orc.solve_adjoint(w.t0, w.tvals, y0, theta, grads, n_threads=cores)
+        else:
+            orc.solve_forward(w.t0, w.tvals, y0, theta, n_threads=cores)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return n_sample / best, cores, best
+
+
+def run_reference(args, w, problem, rank, world):
+    if rank != 0:
+        return
+    n_sample = args.cpu_sample or 4096
+    from oracle.oracle import Oracle, max_threads
+    orc = Oracle(problem, rtol=1e-8, atol=1e-8)
+    y0, theta = w.draws(n_sample)
+    grads = np.ones((len(w.tvals), problem.n_states))
+    cores = max_threads()
+
+    def step():
+        if w.adjoint:
+            orc.solve_adjoint(w.t0, w.tvals, y0, theta, grads, n_threads=cores)
+        else:
+            orc.solve_forward(w.t0, w.tvals, y0, theta, n_threads=cores)
+
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t
+    value = n_sample * args.steps / dt
+    sample = ('%d of the workload\'s %d draws per step, OpenMP over instances on all host threads'
+              % (n_sample, w.batch))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'solves/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': config_dict(w, problem, n_sample, args.gpus, extra={
+            'note': 'CPU restatement of the reference path (oracle/cvodes_port.c); the reference '
+                    'itself needs SUNDIALS, which is absent from this image'}),
+        'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(w, problem, batch, n_gpus, extra=None):
+    cfg = {
+        'workload': w.name,
+        'problem': {'n_states': problem.n_states, 'n_params': problem.n_params_total,
+                    'n_deriv': problem.n_params, 'n_tvals': int(len(w.tvals))},
+        'batch_per_gpu': int(batch), 'global_batch': int(batch) * n_gpus,
+        'rtol': 1e-8, 'atol': 1e-8, 'rtol_backward': 1e-10, 'atol_backward': 1e-10,
+        'method': 'BDF(1-5) + Newton/dense LU; adjoint: backward BDF restarted at every tval + quadrature',
+        'cotangent': 'ones((n_t, n_s)) shared by all instances',
+        'theta': 'theta_med * exp(%g * N(0,1)), seed %d' % (w.sigma, w.seed),
+        'parallelism': 'dp%d (independent draws, contiguous shards)' % n_gpus,
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def main():
+    args = parse_args()
+    from sunode_b200 import examples
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    w = examples.workloads()[args.workload]
+    problem = w.make_problem()
+
+    if args.impl == 'reference':
+        run_reference(args, w, problem, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sunode_b200._engine import PinnedBuffer
+    from sunode_b200.solver import AdjointSolver, Solver
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch or w.batch
+    n_t, n_s, n_all, n_d = len(w.tvals), problem.n_states, problem.n_params_total, problem.n_params
+    y0_h, theta_h = w.draws(B, offset=rank * B)
+    grads_h = np.ones((n_t, n_s))
+    if w.adjoint:
+        solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8,
+                               history_capacity=w.history_capacity, device=local_rank,
+                               block_threads=args.block, min_blocks=args.min_blocks)
+    else:
+        solver = Solver(problem, abstol=1e-8, reltol=1e-8, device=local_rank,
+                        block_threads=args.block, min_blocks=args.min_blocks)
+    eng = solver._engine
+
+    # ---- device-resident inputs / outputs (the `value` leg)
+    y0_d = torch.from_numpy(y0_h).to(dev)
+    theta_d = torch.from_numpy(theta_h).to(dev)
+    grads_d = torch.from_numpy(grads_h).to(dev)
+    y_d = torch.empty((B, n_t, n_s), dtype=torch.float64, device=dev)
+    g_d = torch.empty((B, n_d), dtype=torch.float64, device=dev)
+    l_d = torch.empty((B, n_s), dtype=torch.float64, device=dev)
+    st_d = torch.empty((B,), dtype=torch.int32, device=dev)
+    sf_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    sb_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    gather = world > 1 and not args.no_gather
+    if gather:
+        res_d = torch.empty((B, n_d + n_s), dtype=torch.float64, device=dev)
+        y_all = torch.empty((world * B, n_t, n_s), dtype=torch.float64, device=dev)
+        res_all = torch.empty((world * B, n_d + n_s), dtype=torch.float64, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(stats=False):
+        if w.adjoint:
+            solver.solve_adjoint_batch(w.t0, w.tvals, y0_d, theta_d, grads_d, y_out=y_d,
+                                       grad_out=g_d, lamda_out=l_d, status=st_d,
+                                       stats_fwd=sf_d if stats else None,
+                                       stats_bwd=sb_d if stats else None)
+        else:
+            solver.solve_batch(w.t0, w.tvals, y0_d, theta_d, y_out=y_d, status=st_d,
+                               stats=sf_d if stats else None)
+        if gather:
+            dist.all_gather_into_tensor(y_all, y_d)
+            if w.adjoint:
+                torch.cat([g_d, l_d], dim=1, out=res_d)
+                dist.all_gather_into_tensor(res_all, res_d)
+
+    for i in range(max(args.warmup, 1)):
+        step(stats=(i == 0))
+    torch.cuda.synchronize()
+    n_fail = int((st_d != 0).sum().item())
+    mean_fwd_steps = float(sf_d[:, 0].double().mean().item())
+    mean_bwd_steps = float(sb_d[:, 0].double().mean().item()) if w.adjoint else 0.0
+
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kern_ms = np.zeros((args.steps, 3))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    for k in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations (untimed)
+        starts[k].record()
+        step()
+        ends[k].record()
+        ends[k].synchronize()
+        kern_ms[k] = eng.last_kernel_ms()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    total_ms = float(sum(s.elapsed_time(e) for s, e in zip(starts, ends)))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        fails = torch.tensor([n_fail], dtype=torch.int64, device=dev)
+        dist.all_reduce(fails)
+        n_fail = int(fails.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (the `e2e` leg)
+    e2e = None
+    if not args.no_e2e:
+        pin = {k: PinnedBuffer(s) for k, s in {
+            'y0': (B, n_s), 'theta': (B, n_all), 'grads': (n_t, n_s), 'y': (B, n_t, n_s),
+            'g': (B, n_d), 'l': (B, n_s)}.items()}
+        pin_st = PinnedBuffer((B,), np.int32)
+        pin['y0'].array[...] = y0_h
+        pin['theta'].array[...] = theta_h
+        pin['grads'].array[...] = grads_h
+
+        def e2e_step():
+            if w.adjoint:
+                solver.solve_adjoint_batch(w.t0, w.tvals, pin['y0'].array, pin['theta'].array,
+                                           pin['grads'].array, y_out=pin['y'].array,
+                                           grad_out=pin['g'].array, lamda_out=pin['l'].array,
+                                           status=pin_st.array)
+            else:
+                solver.solve_batch(w.t0, w.tvals, pin['y0'].array, pin['theta'].array,
+                                   y_out=pin['y'].array, status=pin_st.array)
+
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()                     # returns after the D2H copies completed
+        e2e_s = time.perf_counter() - t
+        if world > 1:
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        h2d = 8 * (B * n_s + B * n_all + n_t) + (8 * n_t * n_s if w.adjoint else 0) + 8 * n_s
+        d2h = 8 * B * n_t * n_s + 4 * B + (8 * B * (n_d + n_s) if w.adjoint else 0)
+        assert np.array_equal(pin['y'].array, y_d.cpu().numpy()), 'e2e and device legs disagree'
+        e2e = {'value': world * B * args.steps / e2e_s, 'unit': 'solves/s',
+               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': 1e3 * e2e_s / args.steps,
+               'timer': 'host wall clock around the public API call (includes H2D, kernels, D2H)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')):
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650'
+    bytes_solve = algorithmic_bytes_per_solve(n_s, n_all, n_d, n_t, w.adjoint, mean_fwd_steps)
+    dom = 2 if w.adjoint else 0
+    dom_ms = float(kern_ms[:, dom].mean())
+    achieved = bytes_solve * B / (dom_ms * 1e-3) / 1e9
+    info = eng.kernel_info()
+    roofline = {
+        'bound': 'hbm', 'kernel': 'sb_backward' if w.adjoint else 'sb_forward',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        'traffic': None, 'peak_source': peak_src,
+        'algorithmic_bytes_per_solve': bytes_solve, 'kernel_ms': dom_ms,
+        'kernel_ms_all': {'sb_forward': float(kern_ms[:, 0].mean()),
+                          'sb_tables': float(kern_ms[:, 1].mean()),
+                          'sb_backward': float(kern_ms[:, 2].mean())},
+        'kernel_share_of_step': dom_ms / (total_ms / args.steps),
+        'note': 'the path is FP64-latency bound, not HBM bound (DESIGN.md); frac is reported as '
+                'the contract asks, warp efficiency and FP64 pipe use are in profiles/',
+        'mean_steps': {'forward': mean_fwd_steps, 'backward': mean_bwd_steps},
+        'registers': {'forward': info['regs_fwd'], 'backward': info['regs_bwd']},
+        'block_threads': info['block_threads'],
+        'resident_blocks_per_sm': {'forward': info['blocks_per_sm_fwd'],
+                                   'backward': info['blocks_per_sm_bwd']},
+    }
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'solves/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': config_dict(w, problem, B, world, extra={
+            'l2': 'L2 flushed between timed iterations (512 MiB memset, untimed)',
+            'failed_instances': n_fail,
+            'collective': 'all_gather(y_out) + all_gather(grad|lamda0) per step' if gather else 'none'}),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+    }
+    if not args.no_cpu_baseline:
+        n_sample = args.cpu_sample or min(B, 8192)
+        v, cores, secs = cpu_baseline(w, problem, n_sample, w.adjoint)
+        line['cpu_baseline'] = {
+            'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
+            'sample': 'first %d of the %d draws, OpenMP over instances, %.1f s' % (n_sample, B, secs)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

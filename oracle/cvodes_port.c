@@ -511,7 +511,7 @@ static int cv_nls(cv_mem* m, int nflag) {
         for (int i = 0; i < n; ++i) m->y[i] = m->zn[0][i] + m->acor[i];
         retval = m->f(m, m->tn, m->y, m->ftemp); m->nfe++;
         if (retval < 0) { retval = CV_RHSFUNC_FAIL; goto done; }
-        if (retval > 0) { retval = RHSFUNC_RECVR; goto recover; }
+        if (retval > 0) { retval = RHSFUNC_RECVR; goto done; }   /* Sys failure before the Newton loop: no retry */
         for (int i = 0; i < n; ++i) delta[i] = m->rl1 * m->zn[1][i] + m->acor[i] - m->gamma * m->ftemp[i];
 
         if (callSetup) {
@@ -521,7 +521,7 @@ static int cv_nls(cv_mem* m, int nflag) {
             m->forceSetup = 0;
             m->gamrat = 1.0; m->gammap = m->gamma; m->crate = 1.0; m->nstlp = m->nst;
             if (retval < 0) { retval = CV_LSETUP_FAIL; goto done; }
-            if (retval > 0) { retval = CONV_FAIL; goto recover; }
+            if (retval > 0) { retval = CONV_FAIL; goto done; }
         }
 
         int curiter = 0;
@@ -554,7 +554,6 @@ static int cv_nls(cv_mem* m, int nflag) {
             if (retval > 0) { retval = RHSFUNC_RECVR; break; }
             for (int i = 0; i < n; ++i) delta[i] = m->rl1 * m->zn[1][i] + m->acor[i] - m->gamma * m->ftemp[i];
         }
-recover:
         /* recoverable failure with stale Jacobian: retry once with a fresh one */
         if (retval > 0 && !m->jcur) {
             callSetup = 1;
@@ -1145,7 +1144,11 @@ static int adjoint_backward(const oracle_problem* prob, const oracle_options* op
             double tret = t_upper;
             int ok = 0;
             for (int retry = 0; retry < opt->max_retries_b; ++retry) {
-                m.tstop = t_lower; m.tstopset = 1;  /* CVodeB integrates with tstop = tBout */
+                /* CVodeB sets the stop time of the backward integrator to the start of the current
+                 * checkpoint interval (ck_t0), which with one data segment (solver.py:588) is the
+                 * forward problem's initial time -- not tBout: the integrator steps past t_lower
+                 * and CV_NORMAL interpolates back. */
+                m.tstop = tend; m.tstopset = 1;
                 int r = cv_solve(&m, t_lower, lam, &tret, CV_NORMAL);
                 if (r >= 0) { ok = 1; break; }
                 if (r != CV_TOO_MUCH_WORK) { status = r; break; }

@@ -1,0 +1,72 @@
+// sb_args.h -- kernel argument blocks shared by the host launcher (sb_api.cpp) and the device
+// code (sb_kernels.cuh, compiled by NVRTC).  Plain C structs; 8-byte members first so host and
+// device agree on the layout without packing pragmas.
+#pragma once
+
+#define SB_STATS_STRIDE 8     /* ints per instance: nst nfe nje nsetups netf ncfn nni aux */
+
+/* history point: (t, order, y[NS])                         -> NS + 2 doubles
+ * interpolation table entry for the interval (t_lo, t_hi):
+ *   [0] t_lo [1] t_hi [2] order [3] 1/delt [4..9] T[0..5] [10 + NS*j + k] Y[j][k]  -> 10 + 6*NS */
+#define SB_HIST_STRIDE(ns) ((ns) + 2)
+#define SB_TAB_STRIDE(ns) (10 + 6 * (ns))
+
+typedef struct SbForwardArgs {
+    double t0;
+    double rtol;
+    const double* tvals;      /* [n_t] */
+    const double* y0;         /* [B][NS] */
+    const double* params;     /* [B][NP] */
+    const double* atol;       /* [NS] */
+    double* y_out;            /* [B][n_t][NS] */
+    double* hist;             /* [B][hist_cap][NS+2] or NULL */
+    int* hist_n;              /* [B] number of stored points */
+    int* status;              /* [B] */
+    int* stats;               /* [B][SB_STATS_STRIDE] or NULL */
+    long long B;
+    int n_t;
+    int hist_cap;
+    int max_steps;            /* internal steps allowed per output time */
+    int pad_;
+} SbForwardArgs;
+
+typedef struct SbTablesArgs {
+    const double* hist;
+    const int* hist_n;
+    double* tab;              /* [B][hist_cap][10 + 6*NS] */
+    long long B;
+    int hist_cap;
+    int pad_;
+} SbTablesArgs;
+
+typedef struct SbBackwardArgs {
+    double rtol, atol, rtol_q, atol_q;
+    double t_start;           /* the reference's `t0` argument of solve_backward: the LAST time */
+    double t_end;             /* the reference's `tend`: the initial time */
+    const double* tvals;      /* [n_t] */
+    const double* params;     /* [B][NP] */
+    const double* grads;      /* [B][n_t][NS], or [n_t][NS] when grads_shared */
+    const double* tab;
+    const int* hist_n;
+    const int* fwd_status;    /* [B] or NULL */
+    double* grad_out;         /* [B][ND] */
+    double* lamda_out;        /* [B][NS] */
+    int* status;              /* [B] */
+    int* stats;               /* [B][SB_STATS_STRIDE] or NULL */
+    long long B;
+    int n_t;
+    int hist_cap;
+    int max_steps;            /* internal steps allowed per interval */
+    int grads_shared;
+} SbBackwardArgs;
+
+typedef struct SbEvalArgs {
+    const double* t;          /* [n] */
+    const double* y;          /* [n][NS] */
+    const double* params;     /* [n][NP] or [NP] when params_shared */
+    const double* lam;        /* [n][NS] or NULL */
+    double* out;              /* kind 0: [n][NS] rhs; 1: [n][NS*NS] jac; 2: [n][NS] adj; 3: [n][ND] quad */
+    long long n;
+    int kind;
+    int params_shared;
+} SbEvalArgs;

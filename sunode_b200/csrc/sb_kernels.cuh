@@ -1,0 +1,349 @@
+// sb_kernels.cuh -- kernel entry points.  This file is appended (by #include) to the generated
+// problem functions (sb_rhs, sb_jac, sb_adj_rhs, sb_adj_jac, sb_quad_rhs and SB_NS/SB_NP/SB_ND,
+// see sunode_b200/symode/codegen.py) and compiled as one translation unit for sm_100a, so the
+// problem functions are inlined into the integrator -- the device-side replacement of the
+// reference's numba @cfunc trampolines (/root/reference/sunode/problem.py:156-383).
+//
+//   sb_forward   K1: Solver.solve / AdjointSolver.solve_forward   (solver.py:467-527, 682-721)
+//   sb_tables        interpolation tables for the stored forward steps (CVODES CV_POLYNOMIAL data)
+//   sb_backward  K2: AdjointSolver.solve_backward                  (solver.py:723-784)
+//   sb_eval          batched evaluation of the generated functions (as_pytensor.py:160-183 EvalRhs)
+//
+// One thread integrates one instance; instances are independent, so there is no inter-thread
+// communication at all.  Inputs/outputs are instance-major (a batch-1 view is byte-compatible
+// with the reference's [n_t, n_s] C-order buffers).
+#pragma once
+#include "sb_args.h"
+#include "sb_bdf.cuh"
+
+#ifndef SB_BLOCK
+#define SB_BLOCK 128
+#endif
+#ifndef SB_MIN_BLOCKS
+#define SB_MIN_BLOCKS 1
+#endif
+
+namespace sb {
+
+constexpr int NS = SB_NS;
+constexpr int NP = SB_NP;
+constexpr int ND = SB_ND;
+constexpr int NP_ = SB_NP > 0 ? SB_NP : 1;
+constexpr int ND_ = SB_ND > 0 ? SB_ND : 1;
+constexpr int HIST_STRIDE = SB_HIST_STRIDE(SB_NS);
+constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ------------------------------------------------------------------------------------ forward
+struct FwdSys {
+    double p[NP_];
+    double t;
+    __device__ __forceinline__ void set_time(double t_) { t = t_; }
+    __device__ __forceinline__ void rhs(const double* y, double* out) const { sb_rhs(t, y, p, out); }
+    __device__ __forceinline__ void jac(const double* y, double* J) const { sb_jac(t, y, p, J); }
+    __device__ __forceinline__ void quad(const double*, double*) const {}
+};
+
+__device__ __forceinline__ void store_point(double* hist, int idx, double t, int order, const double* y) {
+    double* e = hist + (size_t)idx * HIST_STRIDE;
+    e[0] = t;
+    e[1] = (double)order;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[2 + i] = y[i];
+}
+
+__device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst) {
+    using Integrator = Bdf<NS, 0, FwdSys>;
+    Integrator bdf;
+    FwdSys sys;
+    double y0[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) y0[i] = a.y0[inst * NS + i];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+    bdf.reltol = a.rtol;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol[i];
+    bdf.reltolQ = 0.0; bdf.abstolQ = 1.0;
+    bdf.clear_stats();
+    bdf.reinit(a.t0, y0, nullptr);
+
+    double* yo = a.y_out + (size_t)inst * a.n_t * NS;
+    double* hist = a.hist ? a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE : nullptr;
+    int status = SB_SUCCESS;
+
+    for (int k = 0; k < a.n_t && status == SB_SUCCESS; ++k) {
+        const double tout = a.tvals[k];
+        if (tout == a.t0) {
+            // the reference writes row 0 here whatever k is (solver.py:505,707)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) yo[i] = y0[i];
+            continue;
+        }
+        bool need_steps = true;
+        if (bdf.nst == 0) {
+            status = bdf.first_call(sys, tout);
+            if (status != SB_SUCCESS) break;
+            if (hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0]);
+        } else if ((bdf.tn - tout) * bdf.h >= 0.0) {
+            need_steps = false;
+        }
+        if (need_steps) {
+            int nloc = 0;
+            for (;;) {
+                if (nloc >= a.max_steps) { status = SB_TOO_MUCH_WORK; break; }
+                if (hist && bdf.nst + 1 >= a.hist_cap) { status = SB_TOO_MUCH_WORK; break; }
+                status = bdf.pre_step_checks();
+                if (status != SB_SUCCESS) break;
+                status = bdf.step(sys);
+                if (status != SB_SUCCESS) break;
+                nloc++;
+                if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
+                if ((bdf.tn - tout) * bdf.h >= 0.0) break;
+            }
+            if (status != SB_SUCCESS) break;
+        }
+        double yk[NS];
+        bdf.get_dky(tout, yk);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) yo[(size_t)k * NS + i] = yk[i];
+    }
+
+    if (status != SB_SUCCESS) {
+        // failed instances read as NaN, like the reference's Ops (as_pytensor.py:289-290)
+        for (int k = 0; k < a.n_t * NS; ++k) yo[k] = qnan();
+    }
+    a.status[inst] = status;
+    if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
+    if (a.stats) {
+        int* s = a.stats + inst * SB_STATS_STRIDE;
+        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = bdf.nst + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------ tables
+// One thread per (instance, interval).  Newton divided differences through the `order + 1` stored
+// points ending at the interval's right end, scaled by the interval length as CVODES does
+// (CVApolynomialGetY); `order` is the BDF order of the step that produced the right end point.
+__device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long long inst, int idx) {
+    const int np = a.hist_n[inst];
+    if (idx < 1 || idx >= np) return;
+    const double* hist = a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE;
+    double* e = a.tab + ((size_t)inst * a.hist_cap + idx) * TAB_STRIDE;
+    int order = (int)hist[(size_t)idx * HIST_STRIDE + 1];
+    if (order > idx) order = idx;
+    if (order < 1) order = 1;
+    double T[SB_LMAX], Y[SB_LMAX][NS];
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j) {
+        if (j <= order) {
+            const double* pnt = hist + (size_t)(idx - j) * HIST_STRIDE;
+            T[j] = pnt[0];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Y[j][k] = pnt[2 + k];
+        } else {
+            T[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Y[j][k] = 0.0;
+        }
+    }
+    const double delt = fabs(T[0] - T[1]);
+#pragma unroll
+    for (int i = 1; i < SB_LMAX; ++i) {
+#pragma unroll
+        for (int j = SB_LMAX - 1; j >= 1; --j) {
+            if (i <= order && j >= i && j <= order) {
+                const double factor = delt / (T[j] - T[j - i]);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) Y[j][k] = factor * (Y[j][k] - Y[j - 1][k]);
+            }
+        }
+    }
+    e[0] = T[1];
+    e[1] = T[0];
+    e[2] = (double)order;
+    e[3] = 1.0 / delt;
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j) e[4 + j] = T[j];
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j)
+#pragma unroll
+        for (int k = 0; k < NS; ++k) e[10 + NS * j + k] = Y[j][k];
+}
+
+// ------------------------------------------------------------------------------------ backward
+struct BwdSys {
+    double p[NP_];
+    const double* tab;     // this instance's table base
+    int np;                // stored points; intervals are 1 .. np-1
+    int idx;               // current interval (CVODES' ilast)
+    double t;
+    double yi[NS];         // forward solution interpolated at t
+
+    __device__ __forceinline__ void set_time(double t_) {
+        t = t_;
+        const double* e = tab + (size_t)idx * TAB_STRIDE;
+        // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
+        if (t < __ldg(e)) {
+            do { --idx; e -= TAB_STRIDE; } while (idx > 1 && t <= __ldg(e));
+            if (idx < 1) { idx = 1; e = tab + TAB_STRIDE; }
+        } else if (t > __ldg(e + 1)) {
+            while (idx < np - 1 && t > __ldg(e + 1)) { ++idx; e += TAB_STRIDE; }
+        }
+        const int order = (int)__ldg(e + 2);
+        const double inv_delt = __ldg(e + 3);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) yi[k] = __ldg(e + 10 + k);
+        double c = 1.0;
+#pragma unroll
+        for (int i = 0; i < SB_QMAX; ++i) {
+            if (i < order) {
+                c *= (t - __ldg(e + 4 + i)) * inv_delt;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) yi[k] = fma(c, __ldg(e + 10 + NS * (i + 1) + k), yi[k]);
+            }
+        }
+    }
+    __device__ __forceinline__ void rhs(const double* lam, double* out) const { sb_adj_rhs(t, yi, lam, p, out); }
+    __device__ __forceinline__ void jac(const double*, double* J) const { sb_adj_jac(t, yi, p, J); }
+    __device__ __forceinline__ void quad(const double* lam, double* out) const { sb_quad_rhs(t, yi, lam, p, out); }
+};
+
+__device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst) {
+    using Integrator = Bdf<NS, ND, BwdSys>;
+    double* gout = a.grad_out + inst * ND;
+    double* lout = a.lamda_out + inst * NS;
+    int status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
+    const int np = a.hist_n[inst];
+    if (status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;   // no forward data
+
+    Integrator bdf;
+    BwdSys sys;
+    double lam[NS], quad[ND_];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lam[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND_; ++i) quad[i] = 0.0;
+    bdf.clear_stats();
+
+    if (status == SB_SUCCESS) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+        sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
+        sys.np = np;
+        sys.idx = np - 1;
+        bdf.reltol = a.rtol;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol;
+        bdf.reltolQ = a.rtol_q; bdf.abstolQ = a.atol_q;
+
+        const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
+        // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
+        for (int k = 0; k <= a.n_t && status == SB_SUCCESS; ++k) {
+            const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
+            const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+            if (t_lower < t_upper) {
+                bdf.reinit(t_upper, lam, quad);          // CVodeReInitB + CVodeQuadReInitB
+                // CVodeB stops the backward integrator at the start of the checkpoint interval,
+                // i.e. the forward problem's initial time; it steps past t_lower and interpolates
+                bdf.tstop = a.t_end; bdf.tstopset = true;
+                status = bdf.first_call(sys, t_lower);
+                if (status != SB_SUCCESS) break;
+                int nloc = 0;
+                for (;;) {
+                    if (nloc >= a.max_steps) { status = SB_TOO_MUCH_WORK; break; }
+                    status = bdf.pre_step_checks();
+                    if (status != SB_SUCCESS) break;
+                    status = bdf.step(sys);
+                    if (status != SB_SUCCESS) break;
+                    nloc++;
+                    bdf.snap_to_tstop();
+                    if ((bdf.tn - t_lower) * bdf.h >= 0.0) break;
+                    bdf.limit_to_tstop();
+                }
+                if (status != SB_SUCCESS) break;
+                bdf.get_dky(t_lower, lam);                // CVodeGetB
+                if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
+            }
+            if (k < a.n_t) {
+                const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) lam[i] -= g[i];
+            }
+        }
+    }
+    if (status != SB_SUCCESS) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) lam[i] = qnan();
+#pragma unroll
+        for (int i = 0; i < ND_; ++i) quad[i] = qnan();
+    }
+#pragma unroll
+    for (int i = 0; i < ND; ++i) gout[i] = quad[i];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lout[i] = lam[i];
+    a.status[inst] = status;
+    if (a.stats) {
+        int* s = a.stats + inst * SB_STATS_STRIDE;
+        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = np;
+    }
+}
+
+}  // namespace sb
+
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_forward(const SbForwardArgs a) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst < a.B) sb::forward_instance(a, inst);
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+sb_tables(const SbTablesArgs a) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long inst = gid / a.hist_cap;
+    const int idx = (int)(gid - inst * a.hist_cap);
+    if (inst < a.B) sb::build_table_entry(a, inst, idx);
+}
+
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_backward(const SbBackwardArgs a) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst < a.B) sb::backward_instance(a, inst);
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+sb_eval(const SbEvalArgs a) {
+    using namespace sb;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double y[NS], p[NP_], lam[NS];
+    const double t = a.t[i];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) { y[k] = a.y[i * NS + k]; lam[k] = a.lam ? a.lam[i * NS + k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = a.params_shared ? a.params[k] : a.params[i * NP + k];
+    if (a.kind == 0) {
+        double out[NS];
+        sb_rhs(t, y, p, out);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
+    } else if (a.kind == 1) {
+        double out[NS * NS];
+        sb_jac(t, y, p, out);
+#pragma unroll
+        for (int k = 0; k < NS * NS; ++k) a.out[i * NS * NS + k] = out[k];
+    } else if (a.kind == 2) {
+        double out[NS];
+        sb_adj_rhs(t, y, lam, p, out);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
+    } else if (a.kind == 3) {
+        double out[ND_];
+        sb_quad_rhs(t, y, lam, p, out);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) a.out[i * ND + k] = out[k];
+    }
+}

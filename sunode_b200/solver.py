@@ -1,0 +1,425 @@
+"""Solver drivers with the reference's surface, running on the B200 engine.
+
+Counterpart of ``sunode/solver.py`` of the reference:
+
+* :class:`Solver` -- ``Solver.__init__`` (solver.py:242-317) and ``Solver.solve`` (:467-527);
+* :class:`AdjointSolver` -- ``AdjointSolver.__init__`` (:531-622), ``solve_forward`` (:682-721)
+  and ``solve_backward`` (:723-784).
+
+The reference drives SUNDIALS CVODES one ``CVode``/``CVodeF``/``CVodeB`` call per output time from
+Python.  Here each of those loops is ONE call into ``libsunode_b200.so`` which runs the whole loop
+inside an sm_100a kernel for a batch of independent instances (``*_batch`` methods); the
+reference-shaped batch-1 methods are the same call with ``B = 1`` and raise
+:class:`~sunode_b200.basic.SolverError` with the reference's messages.  Nothing here falls back
+to a CPU integrator: without a CUDA device every solve raises.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._engine import Engine
+from .basic import CV_TOO_MUCH_WORK, ERRORS, SolverError
+from .problem import Problem
+
+__all__ = ['Solver', 'AdjointSolver', 'SolverError']
+
+
+def _as_dict(data: np.ndarray) -> Dict[str, Any]:
+    if data.dtype.fields is not None:
+        return {name: _as_dict(data[name]) for name in data.dtype.names}
+    if data.shape == ():
+        return data.item()
+    return data
+
+
+def _is_torch(x: Any) -> bool:
+    return type(x).__module__.split('.')[0] == 'torch'
+
+
+class _ParamsMixin:
+    """Parameter plumbing shared by both solvers (reference solver.py:428-465, 650-680)."""
+    _problem: Problem
+    _user_data: np.ndarray
+
+    def as_xarray(self, tvals, out, sens_out=None, unstack_state=True, unstack_params=True):
+        return self._problem.solution_to_xarray(
+            tvals, out, self._user_data, sensitivity=sens_out,
+            unstack_state=unstack_state, unstack_params=unstack_params)
+
+    @property
+    def params_dtype(self):
+        return self._problem.params_dtype
+
+    @property
+    def derivative_params_dtype(self):
+        return self._problem.params_subset.subset_dtype
+
+    @property
+    def remainder_params_dtype(self):
+        return self._problem.params_subset.remainder.subset_dtype
+
+    def set_params(self, params):
+        self._problem.update_params(self._user_data, params)
+
+    def get_params(self):
+        return self._problem.extract_params(self._user_data)
+
+    def set_params_dict(self, params):
+        data = self.get_params()
+        self._problem.params_subset.from_dict(params, data)
+        self.set_params(data)
+
+    def get_params_dict(self):
+        return _as_dict(self.get_params())
+
+    def set_derivative_params(self, params):
+        self._problem.update_subset_params(self._user_data, params)
+
+    def set_remaining_params(self, params):
+        self._problem.update_remaining_params(self._user_data, params)
+
+    # ---- helpers for the batch entry points
+    def _flat_params(self) -> np.ndarray:
+        return self._problem.flat_params(self._user_data)
+
+    def _batch_params(self, params, B: int):
+        """``params`` for a batch call: None -> the solver's current parameters for every
+        instance; a structured array of ``params_dtype`` with shape (B,); or a float64
+        ``[B, n_params_total]`` array / CUDA tensor in declaration order."""
+        n_all = self._problem.n_params_total
+        if params is None:
+            return np.ascontiguousarray(np.broadcast_to(self._flat_params(), (B, n_all)))
+        if _is_torch(params):
+            return params
+        params = np.asarray(params)
+        if params.dtype == self._problem.params_dtype and params.dtype.fields is not None:
+            params = np.ascontiguousarray(params).reshape(-1)
+            if params.dtype.itemsize:
+                params = params.view(np.float64).reshape(params.shape[0], n_all)
+            else:
+                params = np.zeros((params.shape[0], 0))
+        params = np.asarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = np.broadcast_to(params, (B, n_all))
+        return np.ascontiguousarray(params)
+
+    def _flat_state(self, y0) -> np.ndarray:
+        if _is_torch(y0):
+            return y0
+        y0 = np.asarray(y0)
+        if y0.dtype == self._problem.state_dtype and y0.dtype.fields is not None:
+            y0 = np.ascontiguousarray(y0).reshape(-1).view(np.float64).reshape(-1, self._problem.n_states)
+            return y0
+        return y0
+
+
+def _raise_forward(status: int, tvals, y_row) -> None:
+    """Reproduce the reference's error text (solver.py:516-519, 716-719)."""
+    finite = np.isfinite(np.asarray(y_row)).all(axis=-1) if len(tvals) else np.zeros(0, bool)
+    t_fail = tvals[int(np.argmin(finite))] if len(tvals) and not finite.all() else (
+        tvals[-1] if len(tvals) else float('nan'))
+    if status == CV_TOO_MUCH_WORK:
+        raise SolverError(f"Too many solver retries before time={t_fail}.")
+    error = ERRORS.get(int(status), 'UNKNOWN')
+    raise SolverError(f"Solving ode failed before time={t_fail}: {error} ({int(status)})")
+
+
+class Solver(_ParamsMixin):
+    """Forward solver (reference ``Solver``, solver.py:213-527), dense-BDF path.
+
+    Options of the reference that select other SUNDIALS modules are accepted for signature
+    compatibility and rejected with ``NotImplementedError`` when they would change the
+    algorithm (ADAMS, non-dense linear solvers, constraints, forward sensitivities)."""
+
+    def __init__(self, problem: Problem, *, abstol=1e-10, reltol=1e-10,
+                 sens_mode: Optional[str] = None, scaling_factors: Optional[np.ndarray] = None,
+                 constraints: Optional[np.ndarray] = None, solver='BDF', linear_solver='dense',
+                 linear_solver_kwargs=None, device: Optional[int] = None,
+                 block_threads: Optional[int] = None, min_blocks: Optional[int] = None):
+        if linear_solver_kwargs is None:
+            linear_solver_kwargs = {}
+        if solver not in ('BDF', 'ADAMS'):
+            raise ValueError(f'Unknown solver {solver}.')
+        if solver != 'BDF':
+            raise NotImplementedError('Only the BDF method is implemented on the B200 engine.')
+        if linear_solver != 'dense':
+            raise NotImplementedError(
+                'Only linear_solver="dense" (in-register LU with the analytic Jacobian) is implemented.')
+        if sens_mode is not None:
+            raise NotImplementedError('Forward sensitivities are not implemented yet; use AdjointSolver.')
+        if constraints is not None:
+            raise NotImplementedError('Constraints are not implemented.')
+        self._problem = problem
+        self._user_data = problem.make_user_data()
+        self._constraints = constraints
+        self._abstol = abstol
+        self._reltol = reltol
+        self._linear_solver_kind = linear_solver
+        self._linear_solver_kwargs = linear_solver_kwargs
+        self._sens_mode = sens_mode
+        self._solver_kind = solver
+        self._device = device
+        self._launch_cfg = (block_threads, min_blocks)
+        self._mxstep = 500
+        self._state_names = ['_problem', '_user_data', '_constraints', '_abstol', '_reltol',
+                             '_linear_solver_kind', '_linear_solver_kwargs', '_sens_mode',
+                             '_solver_kind', '_device', '_launch_cfg', '_mxstep', '_state_names']
+        self._init_engine()
+
+    def _init_engine(self) -> None:
+        self._compute_sens = False
+        self._engine = Engine(self._problem.generated, device=self._device,
+                              block_threads=self._launch_cfg[0], min_blocks=self._launch_cfg[1])
+        self._set_tolerances(self._abstol, self._reltol)
+
+    # pickling like the reference (solver.py:319-324): configuration only, handle re-created
+    def __getstate__(self):
+        return {name: self.__dict__[name] for name in self._state_names}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._init_engine()
+
+    def _set_tolerances(self, atol=None, rtol=None):
+        atol = np.array(atol, dtype=np.float64)
+        rtol = np.array(rtol, dtype=np.float64)
+        n_states = self._problem.n_states
+        if rtol.ndim != 0:
+            raise NotImplementedError('Vector rtol is not implemented; use a scalar rtol.')
+        if atol.ndim == 1:
+            assert atol.shape == (n_states,)
+        elif atol.ndim != 0:
+            raise ValueError('Invalid tolerance.')
+        self._engine.set_tolerances(float(rtol), atol)
+        self._atol = atol
+        self._rtol = rtol
+
+    def set_max_num_steps(self, mxstep: int) -> None:
+        """``lib.CVodeSetMaxNumSteps(solver._ode, mxstep)`` of the reference README (:248)."""
+        self._mxstep = int(mxstep)
+
+    def make_output_buffers(self, tvals):
+        return np.zeros((len(tvals), self._problem.n_states))
+
+    # ------------------------------------------------------------------ batch-1, reference API
+    def solve(self, t0, tvals, y0, y_out, *, sens0=None, sens_out=None, max_retries=5):
+        n_states = self._problem.n_states
+        y0 = np.asarray(y0)
+        if y0.dtype == self._problem.state_dtype and y0.dtype.fields is not None:
+            y0 = y0[None].view(np.float64)
+        if y0.shape != (n_states,):
+            raise ValueError(f"y0 should have shape {(n_states,)} but has shape {y0.shape}.")
+        tvals = np.asarray(tvals, dtype=np.float64)
+        out, status = self.solve_batch(t0, tvals, y0[None, :], None, max_retries=max_retries)
+        if status[0] != 0:
+            _raise_forward(int(status[0]), tvals, out[0])
+        y_out[...] = out[0]
+
+    # ------------------------------------------------------------------ batched
+    def solve_batch(self, t0, tvals, y0, params=None, y_out=None, *, status=None, stats=None,
+                    max_retries=5, stream=None) -> Tuple[Any, Any]:
+        """Solve ``B`` independent instances: ``y0[B, n_states]``, ``params[B, n_params_total]``
+        (or None for the solver's current parameters).  Returns ``(y_out[B, n_t, n_states],
+        status[B])``; failed instances are NaN rows with a CVODES flag in ``status``."""
+        y0 = self._flat_state(y0)
+        B = int(y0.shape[0])
+        tvals = np.asarray(tvals, dtype=np.float64)
+        params = self._batch_params(params, B)
+        y_out, status = _alloc_like(y0, y_out, (B, len(tvals), self._problem.n_states), status, B)
+        self._engine.set_max_num_steps(self._mxstep, max_retries)
+        self._engine.forward(float(t0), tvals, y0, params, y_out, status, stats,
+                             store_history=False, stream=stream)
+        return y_out, status
+
+
+def _alloc_like(like, out, shape, status, B):
+    if _is_torch(like) and like.is_cuda:
+        import torch
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float64, device=like.device)
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32, device=like.device)
+    else:
+        if out is None:
+            out = np.empty(shape)
+        if status is None:
+            status = np.empty((B,), dtype=np.int32)
+    return out, status
+
+
+def _alloc_out(like, out, shape):
+    if out is not None:
+        return out
+    if _is_torch(like) and like.is_cuda:
+        import torch
+        return torch.empty(shape, dtype=torch.float64, device=like.device)
+    return np.empty(shape)
+
+
+class AdjointSolver(_ParamsMixin):
+    """Forward + adjoint solver (reference ``AdjointSolver``, solver.py:530-784).
+
+    As in the reference the backward problem and its quadrature always run with tolerances
+    1e-10 (solver.py:599,614) unless changed through :meth:`set_backward_tolerances` /
+    :meth:`set_quad_tolerances` -- the counterparts of the raw ``lib.CVodeSStolerancesB`` /
+    ``lib.CVodeQuadSStolerancesB`` pokes shown in the reference README (:243-249)."""
+
+    def __init__(self, problem: Problem, *, abstol=1e-10, reltol=1e-10, checkpoint_n=500_000,
+                 interpolation='polynomial', constraints=None, solver='BDF', adjoint_solver='BDF',
+                 device: Optional[int] = None, history_capacity: Optional[int] = None,
+                 block_threads: Optional[int] = None, min_blocks: Optional[int] = None):
+        if solver not in ('BDF', 'ADAMS'):
+            raise ValueError(f'Unknown solver {solver}.')
+        if adjoint_solver not in ('BDF', 'ADAMS'):
+            raise ValueError(f'Unknown solver {adjoint_solver}.')
+        if solver != 'BDF' or adjoint_solver != 'BDF':
+            raise NotImplementedError('Only the BDF method is implemented on the B200 engine.')
+        if interpolation not in ('polynomial', 'hermite'):
+            assert False
+        if interpolation != 'polynomial':
+            raise NotImplementedError('Only polynomial interpolation of the forward solution is implemented.')
+        if constraints is not None:
+            raise NotImplementedError('Constraints are not implemented.')
+        self._problem = problem
+        self._user_data = problem.make_user_data()
+        self._constraints = constraints
+        self._engine = Engine(problem.generated, device=device, block_threads=block_threads,
+                              min_blocks=min_blocks)
+        # the reference keeps every forward step of one solve in memory (checkpoint_n = 500 000
+        # steps per checkpoint, solver.py:533,588); here the per-instance capacity is explicit
+        self._history_capacity = int(history_capacity or min(int(checkpoint_n), 1024))
+        self._engine.set_history_capacity(self._history_capacity)
+        self._set_tolerances(abstol, reltol)
+        self._engine.set_tolerances_b(1e-10, 1e-10)        # solver.py:599
+        self._engine.set_quad_tolerances_b(1e-10, 1e-10)   # solver.py:614
+        self._mxstep = 500
+        self._mxstep_b = 500
+        self._last_forward: Optional[Tuple[int, int]] = None
+
+    def _set_tolerances(self, atol=None, rtol=None):
+        atol = np.array(atol, dtype=np.float64)
+        rtol = np.array(rtol, dtype=np.float64)
+        if not (atol.ndim in (0, 1) and rtol.ndim == 0):
+            raise ValueError('Invalid tolerance.')
+        self._engine.set_tolerances(float(rtol), atol)
+        self._atol = atol
+        self._rtol = rtol
+
+    def set_backward_tolerances(self, reltol: float, abstol: float) -> None:
+        """``lib.CVodeSStolerancesB(solver._ode, solver._odeB, reltol, abstol)`` (README :246)."""
+        self._engine.set_tolerances_b(reltol, abstol)
+
+    def set_quad_tolerances(self, reltol: float, abstol: float) -> None:
+        """``lib.CVodeQuadSStolerancesB(...)`` (README :247)."""
+        self._engine.set_quad_tolerances_b(reltol, abstol)
+
+    def set_max_num_steps(self, mxstep: int) -> None:
+        self._mxstep = int(mxstep)
+
+    def set_max_num_steps_backward(self, mxstep: int) -> None:
+        self._mxstep_b = int(mxstep)
+
+    def set_history_capacity(self, n_steps: int) -> None:
+        self._history_capacity = int(n_steps)
+        self._engine.set_history_capacity(self._history_capacity)
+
+    def make_output_buffers(self, tvals):
+        y_vals = np.zeros((len(tvals), self._problem.n_states))
+        grad_out = np.zeros(self._problem.n_params)
+        lamda_out = np.zeros(self._problem.n_states)
+        return y_vals, grad_out, lamda_out
+
+    # ------------------------------------------------------------------ batch-1, reference API
+    def solve_forward(self, t0, tvals, y0, y_out, *, max_retries=5):
+        y0 = np.asarray(y0)
+        if y0.dtype == self._problem.state_dtype and y0.dtype.fields is not None:
+            y0 = y0[None].view(np.float64)
+        y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(1, self._problem.n_states)
+        tvals = np.asarray(tvals, dtype=np.float64)
+        out, status = self.solve_forward_batch(t0, tvals, y0, None, max_retries=max_retries)
+        if status[0] != 0:
+            _raise_forward(int(status[0]), tvals, out[0])
+        y_out[...] = out[0]
+
+    def solve_backward(self, t0, tend, tvals, grads, grad_out, lamda_out,
+                       lamda_all_out=None, quad_all_out=None, max_retries=50):
+        if lamda_all_out is not None or quad_all_out is not None:
+            raise NotImplementedError('lamda_all_out / quad_all_out are not implemented.')
+        tvals = np.asarray(tvals, dtype=np.float64)
+        grads = np.ascontiguousarray(grads, dtype=np.float64).reshape(1, len(tvals), self._problem.n_states)
+        g, lam, status = self.solve_backward_batch(t0, tend, tvals, grads, None,
+                                                   max_retries=max_retries)
+        if status[0] != 0:
+            code = int(status[0])
+            if code == CV_TOO_MUCH_WORK:
+                raise SolverError(f"Too many solver retries between time {t0} and {tend}.")
+            raise SolverError(f"Solving ode failed between time {t0} and {tend}: "
+                              f"{ERRORS.get(code, 'UNKNOWN')} ({code})")
+        grad_out[:] = g[0]
+        lamda_out[:] = lam[0]
+
+    # ------------------------------------------------------------------ batched
+    def solve_forward_batch(self, t0, tvals, y0, params=None, y_out=None, *, status=None,
+                            stats=None, max_retries=5, stream=None):
+        """Batched ``solve_forward``; the step history of every instance stays on the device
+        for a following :meth:`solve_backward_batch`."""
+        y0 = self._flat_state(y0)
+        B = int(y0.shape[0])
+        tvals = np.asarray(tvals, dtype=np.float64)
+        params = self._batch_params(params, B)
+        y_out, status = _alloc_like(y0, y_out, (B, len(tvals), self._problem.n_states), status, B)
+        self._engine.set_max_num_steps(self._mxstep, max_retries)
+        self._engine.forward(float(t0), tvals, y0, params, y_out, status, stats,
+                             store_history=True, stream=stream)
+        self._last_forward = (B, len(tvals))
+        return y_out, status
+
+    def solve_backward_batch(self, t0, tend, tvals, grads, params=None, grad_out=None,
+                             lamda_out=None, *, status=None, stats=None, max_retries=50,
+                             stream=None):
+        """Batched ``solve_backward`` on the stored forward pass.  ``t0`` is the LAST time and
+        ``tend`` the initial time, as in the reference (solver.py:723-724).  ``grads`` is
+        ``[B, n_t, n_states]`` or ``[n_t, n_states]`` (shared by all instances).  ``params=None``
+        reuses the parameters of the stored forward pass.  Returns
+        ``(grad_out[B, n_deriv], lamda_out[B, n_states], status[B])``."""
+        if self._last_forward is None:
+            raise SolverError('solve_backward called before solve_forward.')
+        B, n_t = self._last_forward
+        tvals = np.asarray(tvals, dtype=np.float64)
+        if params is not None:
+            params = self._batch_params(params, B)
+        if not _is_torch(grads):
+            grads = np.ascontiguousarray(grads, dtype=np.float64)
+        n_s, n_d = self._problem.n_states, self._problem.n_params
+        grad_out = _alloc_out(grads, grad_out, (B, n_d))
+        lamda_out, status = _alloc_like(grads, lamda_out, (B, n_s), status, B)
+        self._engine.set_max_num_steps_b(self._mxstep_b, max_retries)
+        self._engine.backward(float(t0), float(tend), tvals, params, grads, grad_out, lamda_out,
+                              status, stats, stream=stream)
+        return grad_out, lamda_out, status
+
+    def solve_adjoint_batch(self, t0, tvals, y0, params, grads, *, y_out=None, grad_out=None,
+                            lamda_out=None, status=None, stats_fwd=None, stats_bwd=None,
+                            max_retries=5, max_retries_backward=50, stream=None):
+        """``solve_forward`` followed by ``solve_backward(tvals[-1], t0, tvals, grads, ...)`` for a
+        batch, as one library call (inputs uploaded once).  Returns
+        ``(y_out, grad_out, lamda_out, status)``."""
+        y0 = self._flat_state(y0)
+        B = int(y0.shape[0])
+        tvals = np.asarray(tvals, dtype=np.float64)
+        params = self._batch_params(params, B)
+        if not _is_torch(grads):
+            grads = np.ascontiguousarray(grads, dtype=np.float64)
+        n_s, n_d = self._problem.n_states, self._problem.n_params
+        y_out, status = _alloc_like(y0, y_out, (B, len(tvals), n_s), status, B)
+        grad_out = _alloc_out(y0, grad_out, (B, n_d))
+        lamda_out = _alloc_out(y0, lamda_out, (B, n_s))
+        self._engine.set_max_num_steps(self._mxstep, max_retries)
+        self._engine.set_max_num_steps_b(self._mxstep_b, max_retries_backward)
+        self._engine.adjoint(float(t0), tvals, y0, params, grads, y_out, grad_out, lamda_out,
+                             status, stats_fwd, stats_bwd, stream=stream)
+        self._last_forward = (B, len(tvals))
+        return y_out, grad_out, lamda_out, status

@@ -1,0 +1,120 @@
+"""Host emulation of the device code (test infrastructure, see cuda_shim.h).
+
+Builds the generated ``__device__`` functions together with ``sb_kernels.cuh`` with g++ and runs
+the per-instance integrators on the CPU, so that the CPU-only test tier can compare the *device*
+integrator logic with the oracle.  Nothing in the product imports this.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.normpath(os.path.join(_HERE, '..', '..', 'sunode_b200', 'csrc'))
+_DP = ctypes.POINTER(ctypes.c_double)
+_IP = ctypes.POINTER(ctypes.c_int)
+STATS = 8
+
+
+class ForwardArgs(ctypes.Structure):
+    _fields_ = [('t0', ctypes.c_double), ('rtol', ctypes.c_double), ('tvals', _DP), ('y0', _DP),
+                ('params', _DP), ('atol', _DP), ('y_out', _DP), ('hist', _DP), ('hist_n', _IP),
+                ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong), ('n_t', ctypes.c_int),
+                ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int), ('pad_', ctypes.c_int)]
+
+
+class TablesArgs(ctypes.Structure):
+    _fields_ = [('hist', _DP), ('hist_n', _IP), ('tab', _DP), ('B', ctypes.c_longlong),
+                ('hist_cap', ctypes.c_int), ('pad_', ctypes.c_int)]
+
+
+class BackwardArgs(ctypes.Structure):
+    _fields_ = [('rtol', ctypes.c_double), ('atol', ctypes.c_double), ('rtol_q', ctypes.c_double),
+                ('atol_q', ctypes.c_double), ('t_start', ctypes.c_double),
+                ('t_end', ctypes.c_double), ('tvals', _DP), ('params', _DP), ('grads', _DP),
+                ('tab', _DP), ('hist_n', _IP), ('fwd_status', _IP), ('grad_out', _DP),
+                ('lamda_out', _DP), ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong),
+                ('n_t', ctypes.c_int), ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
+                ('grads_shared', ctypes.c_int)]
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_DP)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(_IP)
+
+
+class Emulator:
+    def __init__(self, problem, workdir):
+        gen = problem.generated
+        self.ns, self.np, self.nd = gen.n_states, gen.n_params, gen.n_deriv
+        os.makedirs(workdir, exist_ok=True)
+        inc = os.path.join(workdir, 'generated_problem.inc')
+        with open(inc, 'w') as fh:
+            fh.write(gen.cuda)
+        out = os.path.join(workdir, 'emu_%s.so' % gen.digest)
+        cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+        cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off',
+               '-I', workdir, '-I', _HERE, '-I', _CSRC, os.path.join(_HERE, 'emu_main.cpp'),
+               '-o', out]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('emulation build failed:\n' + proc.stderr)
+        self.lib = ctypes.CDLL(out)
+
+    def _prep(self, y0, params):
+        y0 = np.atleast_2d(np.asarray(y0, dtype=np.float64))
+        params = np.asarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None]
+        B = max(len(y0), len(params))
+        y0 = np.ascontiguousarray(np.broadcast_to(y0, (B, self.ns)))
+        params = np.ascontiguousarray(np.broadcast_to(params, (B, self.np))) if self.np else np.zeros((B, 1))
+        return y0, params, B
+
+    def forward(self, t0, tvals, y0, params, rtol, atol, hist_cap=0, max_steps=2500):
+        tvals = np.ascontiguousarray(tvals, dtype=np.float64)
+        y0, params, B = self._prep(y0, params)
+        n_t = len(tvals)
+        atol = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=np.float64), (self.ns,)))
+        y_out = np.zeros((B, n_t, self.ns))
+        status = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, STATS), dtype=np.int32)
+        hist = np.zeros((B, hist_cap, self.ns + 2)) if hist_cap else None
+        hist_n = np.zeros(B, dtype=np.int32)
+        a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
+                        _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,
+                        max_steps, 0)
+        self.lib.emu_forward(ctypes.byref(a))
+        return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
+                    params=params, tvals=tvals)
+
+    def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
+                rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000):
+        fwd = self.forward(t0, tvals, y0, params, rtol, atol, hist_cap=hist_cap,
+                           max_steps=2 ** 30)
+        B = len(fwd['status'])
+        n_t = len(fwd['tvals'])
+        tab = np.zeros((B, hist_cap, 10 + 6 * self.ns))
+        ta = TablesArgs(_dp(fwd['hist']), _ip(fwd['hist_n']), _dp(tab), B, hist_cap, 0)
+        self.lib.emu_tables(ctypes.byref(ta))
+        grads = np.ascontiguousarray(grads, dtype=np.float64)
+        shared = int(grads.ndim == 2)
+        grad_out = np.zeros((B, max(self.nd, 1)))[:, :self.nd].copy() if self.nd else np.zeros((B, 0))
+        grad_out = np.ascontiguousarray(grad_out)
+        lam_out = np.zeros((B, self.ns))
+        status = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, STATS), dtype=np.int32)
+        gptr = _dp(grad_out) if self.nd else _dp(np.zeros(1))
+        ba = BackwardArgs(rtol_b, atol_b, rtol_q, atol_q, float(fwd['tvals'][-1]), float(t0),
+                          _dp(fwd['tvals']), _dp(fwd['params']), _dp(grads), _dp(tab),
+                          _ip(fwd['hist_n']), _ip(fwd['status']), gptr, _dp(lam_out),
+                          _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared)
+        self.lib.emu_backward(ctypes.byref(ba))
+        return dict(y=fwd['y'], grad=grad_out, lamda=lam_out, status=status, stats=stats,
+                    fwd=fwd, tab=tab)

@@ -1,0 +1,21 @@
+// Entry points of the host emulation build: loop over instances instead of launching a grid.
+#include "cuda_shim.h"
+#include "generated_problem.inc"     // generated __device__ functions + SB_NS/SB_NP/SB_ND
+#include "sb_kernels.cuh"
+
+extern "C" {
+void emu_forward(const SbForwardArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i) sb::forward_instance(*a, i);
+}
+void emu_tables(const SbTablesArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i)
+        for (int idx = 0; idx < a->hist_cap; ++idx) sb::build_table_entry(*a, i, idx);
+}
+void emu_backward(const SbBackwardArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i) sb::backward_instance(*a, i);
+}
+int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
+}

@@ -1,0 +1,185 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI exactly as a user
+would (``Solver`` / ``AdjointSolver``), against the CPU oracle on the same seeded inputs.
+
+Tolerances.  Both sides implement the same algorithm (CVODES-style BDF) in double precision but
+with different operation order / FMA contraction, so they agree to rounding level only as long as
+they take the same step sequence; for non-stiff problems they do (difference << 1 tolerance
+unit), for the stiff Robertson problem the sequences decorrelate and each side is only within the
+solver's *global* error of the truth.  The tests therefore check
+  (i)  GPU vs oracle:   |y_gpu - y_cpu| <= ENV * (rtol*|y| + atol)   with ENV stated per problem,
+  (ii) gradients:       rel. error <= 1e-5 at rtol = atol = 1e-8 (backward tolerances 1e-10, as
+                        the reference hard-codes, solver.py:599,614), measured against the
+                        column scale of the batch.
+"""
+import numpy as np
+import pytest
+
+from sunode_b200 import examples
+from sunode_b200.solver import AdjointSolver, Solver, SolverError
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(problem, **kw):
+    from oracle.oracle import Oracle
+    return Oracle(problem, **kw)
+
+
+CASES = {
+    # name: (batch, trajectory envelope in tolerance units, gradient rtol)
+    'lv_adj': (512, 1.0, 1e-7),
+    'seir_adj': (256, 1.0, 1e-7),
+    'robertson_adj': (128, 1000.0, 1e-5),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_forward_matches_oracle(name):
+    B, env, _ = CASES[name]
+    w = examples.workloads()[name]
+    prob = w.make_problem()
+    y0, theta = w.draws(B)
+    solver = Solver(prob, abstol=1e-8, reltol=1e-8)
+    stats = np.zeros((B, 8), dtype=np.int32)
+    y, status = solver.solve_batch(w.t0, w.tvals, y0, theta, stats=stats)
+    yo, so, sto = _oracle(prob, rtol=1e-8, atol=1e-8).solve_forward(w.t0, w.tvals, y0, theta)
+    assert (status == 0).all() and (so == 0).all()
+    tol = 1e-8 * np.abs(yo) + 1e-8
+    assert np.max(np.abs(y - yo) / tol) <= env
+    if env <= 1.0:
+        # same step sequence => same counters
+        np.testing.assert_array_equal(stats[:, 0], sto[:, 0])
+        np.testing.assert_array_equal(stats[:, 1], sto[:, 1])
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_adjoint_matches_oracle(name):
+    B, env, grtol = CASES[name]
+    w = examples.workloads()[name]
+    prob = w.make_problem()
+    y0, theta = w.draws(B)
+    rng = np.random.default_rng(7)
+    grads = rng.standard_normal((B, len(w.tvals), prob.n_states))
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=w.history_capacity)
+    y, g, lam, status = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    yo, go, lo, so, _ = _oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(
+        w.t0, w.tvals, y0, theta, grads)
+    assert (status == 0).all() and (so == 0).all()
+    tol = 1e-8 * np.abs(yo) + 1e-8
+    assert np.max(np.abs(y - yo) / tol) <= env
+    assert np.max(np.abs(g - go) / np.abs(go).max(axis=0)) <= grtol
+    assert np.max(np.abs(lam - lo) / np.abs(lo).max(axis=0)) <= max(grtol, 1e-4 if env > 1 else grtol)
+
+
+def test_separate_forward_backward_equals_fused():
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    B = 96
+    y0, theta = w.draws(B)
+    grads = np.ones((len(w.tvals), prob.n_states))      # shared cotangent, test_solve.py:99
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    y1, st1 = solver.solve_forward_batch(w.t0, w.tvals, y0, theta)
+    g1, l1, sb1 = solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
+    y2, g2, l2, st2 = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert (st1 == 0).all() and (sb1 == 0).all() and (st2 == 0).all()
+    np.testing.assert_array_equal(y1, y2)
+    np.testing.assert_array_equal(g1, g2)
+    np.testing.assert_array_equal(l1, l2)
+
+
+def test_reference_shaped_batch1_api():
+    """The reference's smoke test (sunode/test_solve.py:81-154) with numbers attached:
+    x' = x + b has the closed form x(t) = (1 + b) e^t - b."""
+    from sunode_b200 import SympyProblem
+
+    def rhs(t, y, p):
+        return {'x': y.x + p.a.b}
+
+    prob = SympyProblem({'a': {'b': ()}}, {'x': ()}, rhs, [('a', 'b')])
+    b = 0.2
+    time = np.linspace(0, 1)
+    y0 = np.ones((1,), dtype=prob.state_dtype)[0]
+    y0['x'] = 1.0
+
+    solver = Solver(prob)
+    solver.set_params_dict({'a': {'b': b}})
+    out = solver.make_output_buffers(time)
+    solver.solve(0, time, np.ones(1), out)
+    np.testing.assert_allclose(out[:, 0], (1 + b) * np.exp(time) - b, rtol=1e-7)
+    out2 = solver.make_output_buffers(time)
+    solver.solve(0, time, y0, out2)           # structured scalar y0 (solver.py:489-490)
+    np.testing.assert_array_equal(out, out2)
+    with pytest.raises(ValueError):
+        solver.solve(0, time, np.ones(2), out)
+
+    adj = AdjointSolver(prob)
+    adj.set_params_dict({'a': {'b': b}})
+    y_out, grad_out, lamda_out = adj.make_output_buffers(time)
+    adj.solve_forward(0, time, np.ones(1), y_out)
+    grads = np.ones_like(y_out)
+    adj.solve_backward(time[-1], 0, time, grads, grad_out, lamda_out)
+    np.testing.assert_allclose(y_out[:, 0], (1 + b) * np.exp(time) - b, rtol=1e-7)
+    np.testing.assert_allclose(grad_out[0], np.sum(np.exp(time) - 1), rtol=1e-6)
+    np.testing.assert_allclose(-lamda_out[0], np.sum(np.exp(time)), rtol=1e-6)
+
+
+def test_failed_instances_are_nan_with_cvodes_flag():
+    """A draw that blows up (finite-time singularity) must not poison its neighbours: NaN rows and
+    a CVODES flag for that instance only (as_pytensor.py:287-290 semantics, per instance)."""
+    from sunode_b200 import SympyProblem
+
+    def rhs(t, y, p):
+        return {'x': p.k * y.x ** 2}
+
+    prob = SympyProblem({'k': ()}, {'x': ()}, rhs, [('k',)])
+    solver = Solver(prob, abstol=1e-8, reltol=1e-8)
+    tvals = np.linspace(0.1, 2, 20)
+    y0 = np.ones((3, 1))
+    k = np.array([[0.1], [1.0], [0.2]])                  # x blows up at t = 1/k -> only k = 1 fails
+    y, status = solver.solve_batch(0.0, tvals, y0, k)
+    assert status[0] == 0 and status[2] == 0 and status[1] < 0
+    assert np.isnan(y[1]).all()
+    np.testing.assert_allclose(y[0, :, 0], 1 / (1 - 0.1 * tvals), rtol=1e-6)
+    with pytest.raises(SolverError):
+        solver.set_params(np.array((1.0,), dtype=prob.params_dtype)[()])
+        solver.solve(0.0, tvals, np.ones(1), solver.make_output_buffers(tvals))
+
+
+def test_device_tensors_run_in_place():
+    torch = pytest.importorskip('torch')
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    B = 256
+    y0, theta = w.draws(B)
+    grads = np.ones((len(w.tvals), prob.n_states))
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    y_h, g_h, l_h, s_h = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    dev = torch.device('cuda:0')
+    y_d, g_d, l_d, s_d = solver.solve_adjoint_batch(
+        w.t0, w.tvals, torch.from_numpy(y0).to(dev), torch.from_numpy(theta).to(dev),
+        torch.from_numpy(grads).to(dev))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(y_d.cpu().numpy(), y_h)
+    np.testing.assert_array_equal(g_d.cpu().numpy(), g_h)
+    np.testing.assert_array_equal(l_d.cpu().numpy(), l_h)
+    assert (s_d.cpu().numpy() == 0).all()
+
+
+def test_full_size_properties_lv():
+    """BASELINE config 3 at full size (B = 65 536): every instance succeeds, outputs are finite,
+    identical draws give identical results (no cross-instance interference), and the gradient
+    is linear in the cotangent (adjoint linearity)."""
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws()
+    theta[1::2] = theta[0::2]                            # pairs of identical draws
+    g1 = np.ones((len(w.tvals), prob.n_states))
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    y, g, lam, status = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, g1)
+    assert (status == 0).all()
+    assert np.isfinite(y).all() and np.isfinite(g).all() and np.isfinite(lam).all()
+    np.testing.assert_array_equal(y[0::2], y[1::2])
+    np.testing.assert_array_equal(g[0::2], g[1::2])
+    _, g3, lam3, _ = solver.solve_adjoint_batch(w.t0, w.tvals, y0[:4096], theta[:4096], 3.0 * g1)
+    np.testing.assert_allclose(g3, 3.0 * g[:4096], rtol=2e-6, atol=1e-9 * np.abs(g).max())
+    np.testing.assert_allclose(lam3, 3.0 * lam[:4096], rtol=2e-6, atol=1e-9 * np.abs(lam).max())
