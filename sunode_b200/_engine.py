@@ -21,7 +21,7 @@ from ._cache import atomic_write, cache_dir
 from .symode.codegen import GeneratedSource
 
 DEFAULT_ARCH = 'sm_100a'
-DEFAULT_BLOCK = int(os.environ.get('SUNODE_B200_BLOCK', '64'))
+DEFAULT_BLOCK = int(os.environ.get('SUNODE_B200_BLOCK', '32'))
 DEFAULT_MIN_BLOCKS = int(os.environ.get('SUNODE_B200_MIN_BLOCKS', '1'))
 
 _kernel_hash: Optional[str] = None

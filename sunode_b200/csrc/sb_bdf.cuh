@@ -40,6 +40,7 @@
 #define SB_BAD_T (-25)
 #define SB_TOO_CLOSE (-27)
 #define SB_GETY_BADT (-107)
+#define SB_TRY_AGAIN 5          /* internal: attempt() wants another pass */
 
 namespace sb {
 
@@ -177,6 +178,11 @@ struct Bdf {
     // counters
     int nst, nstlp, nstlj;
     Stats st;
+    // a step in flight (cvStep's locals): one call of attempt() is one pass of cvStep's retry loop,
+    // so that the lanes of a warp can be re-converged between passes by the caller
+    double step_t0;
+    int ncf, nef, nefQ, nflag;
+    bool in_step;
 
     // ------------------------------------------------------------------ (re)initialisation
     // CVodeReInit (+ CVodeQuadReInit): order 1, fresh controller state, counters cleared
@@ -200,6 +206,7 @@ struct Bdf {
         saved_tq5 = 0.0; jcur = false; crate = 1.0; delp = 0.0; acnrm = 0.0;
         tstopset = false; tstop = 0.0;
         h = hprime = hscale = 0.0; eta = 1.0; gamma = gammap = gamrat = 1.0; rl1 = 1.0;
+        in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL;
     }
 
     __device__ __forceinline__ void clear_stats() {
@@ -785,67 +792,76 @@ struct Bdf {
     }
 
     // ------------------------------------------------------------------ one internal step (cvStep)
-    __device__ __forceinline__ int step(Sys& sys) {
-        const double saved_t = tn;
-        int ncf = 0, nef = 0, nefQ = 0, nflag = FIRST_CALL;
-        double dsm = 0.0;
-        if (nst > 0 && hprime != h) adjust_params();
-        for (;;) {
-            predict();
-            set_coeffs();
-            const int nr = nls(sys, nflag);
-            if (nr != 0) {
+    // One pass of cvStep's predict / solve / test loop.  Returns SB_SUCCESS when the step is
+    // complete, SB_TRY_AGAIN when the pass failed recoverably (the history has been restored and
+    // rescaled; call again), < 0 on a fatal failure.
+    __device__ __forceinline__ int attempt(Sys& sys) {
+        if (!in_step) {
+            step_t0 = tn;
+            ncf = 0; nef = 0; nefQ = 0; nflag = FIRST_CALL;
+            if (nst > 0 && hprime != h) adjust_params();
+            in_step = true;
+        }
+        predict();
+        set_coeffs();
+        const int nr = nls(sys, nflag);
+        if (nr != 0) {
+            st.ncfn++; ncf++;
+            restore(step_t0);
+            etamax = 1.0;
+            if (ncf == MXNCF) { in_step = false; return SB_CONV_FAILURE; }
+            eta = ETACF;
+            nflag = PREV_CONV_FAIL;
+            rescale();
+            return SB_TRY_AGAIN;
+        }
+        double dsm = acnrm * tq[2];
+        if (!(dsm <= 1.0)) {
+            nef++;
+            nflag = PREV_ERR_FAIL;
+            const int r = error_test_failed(sys, step_t0, dsm, nef);
+            if (r < 0) { in_step = false; return r; }
+            return SB_TRY_AGAIN;
+        }
+        if (QUAD) {
+            ncf = 0; nef = 0;
+            double fq[NQ_];
+            sys.quad(ycur, fq);
+            if (!all_finite<NQ_>(fq)) {
                 st.ncfn++; ncf++;
-                restore(saved_t);
+                restore(step_t0);
                 etamax = 1.0;
-                if (ncf == MXNCF) return SB_CONV_FAILURE;
+                if (ncf == MXNCF) { in_step = false; return SB_REPTD_RHSFUNC_ERR; }
                 eta = ETACF;
                 nflag = PREV_CONV_FAIL;
                 rescale();
-                continue;
+                return SB_TRY_AGAIN;
             }
-            dsm = acnrm * tq[2];
-            if (!(dsm <= 1.0)) {
-                nef++;
-                nflag = PREV_ERR_FAIL;
-                const int r = error_test_failed(sys, saved_t, dsm, nef);
-                if (r < 0) return r;
-                continue;
-            }
-            if (QUAD) {
-                ncf = 0; nef = 0;
-                double fq[NQ_];
-                sys.quad(ycur, fq);
-                if (!all_finite<NQ_>(fq)) {
-                    st.ncfn++; ncf++;
-                    restore(saved_t);
-                    etamax = 1.0;
-                    if (ncf == MXNCF) return SB_REPTD_RHSFUNC_ERR;
-                    eta = ETACF;
-                    nflag = PREV_CONV_FAIL;
-                    rescale();
-                    continue;
-                }
 #pragma unroll
-                for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
-                const double dsmQ = wrms<NQ_>(acorQ, ewtQ) * tq[2];
-                if (!(dsmQ <= 1.0)) {
-                    nefQ++;
-                    nflag = PREV_ERR_FAIL;
-                    const int r = error_test_failed(sys, saved_t, dsmQ, nefQ);
-                    if (r < 0) return r;
-                    continue;
-                }
-                dsm = fmax(dsm, dsmQ);
+            for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
+            const double dsmQ = wrms<NQ_>(acorQ, ewtQ) * tq[2];
+            if (!(dsmQ <= 1.0)) {
+                nefQ++;
+                nflag = PREV_ERR_FAIL;
+                const int r = error_test_failed(sys, step_t0, dsmQ, nefQ);
+                if (r < 0) { in_step = false; return r; }
+                return SB_TRY_AGAIN;
             }
-            break;
+            dsm = fmax(dsm, dsmQ);
         }
         complete_step();
         prepare_next_step(dsm);
         etamax = (nst <= SMALL_NST) ? ETAMX2 : ETAMX3;
         // (CVODES rescales acor by tq[2] here to expose the local error estimate; nothing on this
         // path reads it before the next step overwrites it, so it is not materialised.)
+        in_step = false;
         return SB_SUCCESS;
+    }
+
+    __device__ __forceinline__ int step(Sys& sys) {
+        int r;
+        do { r = attempt(sys); } while (r == SB_TRY_AGAIN);
+        return r;
     }
 
     // ------------------------------------------------------------------ dense output

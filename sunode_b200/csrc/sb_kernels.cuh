@@ -35,6 +35,15 @@ constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// warp vote / convergence point (all 32 lanes of every warp take part, see forward_instance)
+#ifndef SB_HOST_EMULATION
+__device__ __forceinline__ bool sb_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
+__device__ __forceinline__ void sb_converge() { __syncwarp(0xffffffffu); }
+#else
+inline bool sb_any(bool pred) { return pred; }
+inline void sb_converge() {}
+#endif
+
 // ------------------------------------------------------------------------------------ forward
 struct FwdSys {
     double p[NP_];
@@ -53,11 +62,21 @@ __device__ __forceinline__ void store_point(double* hist, int idx, double t, int
     for (int i = 0; i < NS; ++i) e[2 + i] = y[i];
 }
 
-__device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst) {
+// Warp-synchronous driver.  ptxas does not re-converge the lanes of a warp after loops whose trip
+// count differs per lane (every lane ends up running alone, 1/32 of the issue rate), so the loops
+// over internal steps are made warp-uniform by hand: every pass starts with a warp vote, which is
+// also the point where lanes that took different paths through the previous pass meet again.
+// `valid` is false for the padding lanes of the last warp; they vote and do nothing else.
+//
+// Forward: the k-loop over output times of the reference (solver.py:503-521, 705-721) is flattened
+// into the step loop -- a lane emits every output time it has already stepped past and then
+// takes its next step -- so that lanes do not wait for each other at every output time.
+__device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst, bool valid) {
     using Integrator = Bdf<NS, 0, FwdSys>;
     Integrator bdf;
     FwdSys sys;
     double y0[NS];
+    if (!valid) inst = 0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) y0[i] = a.y0[inst * NS + i];
 #pragma unroll
@@ -72,47 +91,60 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
     double* yo = a.y_out + (size_t)inst * a.n_t * NS;
     double* hist = a.hist ? a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE : nullptr;
     int status = SB_SUCCESS;
+    int k = 0;          // next output time
+    int nloc = 0;       // internal steps taken towards tvals[k] (CVode's nstloc, summed over retries)
 
-    for (int k = 0; k < a.n_t && status == SB_SUCCESS; ++k) {
-        const double tout = a.tvals[k];
-        if (tout == a.t0) {
-            // the reference writes row 0 here whatever k is (solver.py:505,707)
-#pragma unroll
-            for (int i = 0; i < NS; ++i) yo[i] = y0[i];
-            continue;
-        }
-        bool need_steps = true;
-        if (bdf.nst == 0) {
-            status = bdf.first_call(sys, tout);
-            if (status != SB_SUCCESS) break;
-            if (hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0]);
-        } else if ((bdf.tn - tout) * bdf.h >= 0.0) {
-            need_steps = false;
-        }
-        if (need_steps) {
-            int nloc = 0;
+    for (;;) {
+        bool work = valid && status == SB_SUCCESS && k < a.n_t;
+        if (work) {
+            // emit the output times that need no further step
             for (;;) {
-                if (nloc >= a.max_steps) { status = SB_TOO_MUCH_WORK; break; }
-                if (hist && bdf.nst + 1 >= a.hist_cap) { status = SB_TOO_MUCH_WORK; break; }
-                status = bdf.pre_step_checks();
-                if (status != SB_SUCCESS) break;
-                status = bdf.step(sys);
-                if (status != SB_SUCCESS) break;
+                const double tout = a.tvals[k];
+                if (tout == a.t0) {
+                    // the reference writes row 0 here whatever k is (solver.py:505,707)
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) yo[i] = y0[i];
+                } else if (bdf.nst > 0 && (bdf.tn - tout) * bdf.h >= 0.0) {
+                    double yk[NS];
+                    bdf.get_dky(tout, yk);
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) yo[(size_t)k * NS + i] = yk[i];
+                } else {
+                    break;
+                }
+                nloc = 0;
+                if (++k == a.n_t) { work = false; break; }
+            }
+        }
+        if (!sb_any(work)) break;
+        if (work) {
+            const double tout = a.tvals[k];
+            if (bdf.nst == 0 && !bdf.in_step) {
+                status = bdf.first_call(sys, tout);
+                if (status == SB_SUCCESS && hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0]);
+            }
+            if (status == SB_SUCCESS && !bdf.in_step) {
+                if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                else if (hist && bdf.nst + 1 >= a.hist_cap) status = SB_TOO_MUCH_WORK;
+                else status = bdf.pre_step_checks();
+            }
+        }
+        sb_converge();
+        if (work && status == SB_SUCCESS) {
+            const int r = bdf.attempt(sys);
+            if (r == SB_SUCCESS) {
                 nloc++;
                 if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
-                if ((bdf.tn - tout) * bdf.h >= 0.0) break;
+            } else if (r != SB_TRY_AGAIN) {
+                status = r;
             }
-            if (status != SB_SUCCESS) break;
         }
-        double yk[NS];
-        bdf.get_dky(tout, yk);
-#pragma unroll
-        for (int i = 0; i < NS; ++i) yo[(size_t)k * NS + i] = yk[i];
     }
+    if (!valid) return;
 
     if (status != SB_SUCCESS) {
         // failed instances read as NaN, like the reference's Ops (as_pytensor.py:289-290)
-        for (int k = 0; k < a.n_t * NS; ++k) yo[k] = qnan();
+        for (int j = 0; j < a.n_t * NS; ++j) yo[j] = qnan();
     }
     a.status[inst] = status;
     if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
@@ -211,8 +243,13 @@ struct BwdSys {
     __device__ __forceinline__ void quad(const double* lam, double* out) const { sb_quad_rhs(t, yi, lam, p, out); }
 };
 
-__device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst) {
+// Backward: the reference restarts the backward integrator at every output time
+// (CVodeReInitB + CVodeQuadReInitB, solver.py:756-757), so the interval loop stays and the lanes of
+// a warp -- which share tvals -- walk the intervals together; only the step loop inside an interval
+// is vote-driven.
+__device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst, bool valid) {
     using Integrator = Bdf<NS, ND, BwdSys>;
+    if (!valid) inst = 0;
     double* gout = a.grad_out + inst * ND;
     double* lout = a.lamda_out + inst * NS;
     int status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
@@ -228,52 +265,66 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     for (int i = 0; i < ND_; ++i) quad[i] = 0.0;
     bdf.clear_stats();
 
-    if (status == SB_SUCCESS) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
-        sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
-        sys.np = np;
-        sys.idx = np - 1;
-        bdf.reltol = a.rtol;
+    for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+    sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
+    sys.np = np;
+    sys.idx = np > 1 ? np - 1 : 1;
+    sys.t = 0.0;
+    bdf.reltol = a.rtol;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol;
-        bdf.reltolQ = a.rtol_q; bdf.abstolQ = a.atol_q;
+    for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol;
+    bdf.reltolQ = a.rtol_q; bdf.abstolQ = a.atol_q;
+    bdf.reinit(a.t_start, lam, quad);
 
-        const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
-        // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
-        for (int k = 0; k <= a.n_t && status == SB_SUCCESS; ++k) {
-            const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
-            const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
-            if (t_lower < t_upper) {
-                bdf.reinit(t_upper, lam, quad);          // CVodeReInitB + CVodeQuadReInitB
+    const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
+    // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
+    for (int k = 0; k <= a.n_t; ++k) {
+        const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
+        const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+        if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
+            const bool live = valid && status == SB_SUCCESS;
+            if (live) {
+                bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
                 // CVodeB stops the backward integrator at the start of the checkpoint interval,
                 // i.e. the forward problem's initial time; it steps past t_lower and interpolates
                 bdf.tstop = a.t_end; bdf.tstopset = true;
                 status = bdf.first_call(sys, t_lower);
-                if (status != SB_SUCCESS) break;
-                int nloc = 0;
-                for (;;) {
-                    if (nloc >= a.max_steps) { status = SB_TOO_MUCH_WORK; break; }
-                    status = bdf.pre_step_checks();
-                    if (status != SB_SUCCESS) break;
-                    status = bdf.step(sys);
-                    if (status != SB_SUCCESS) break;
-                    nloc++;
-                    bdf.snap_to_tstop();
-                    if ((bdf.tn - t_lower) * bdf.h >= 0.0) break;
-                    bdf.limit_to_tstop();
+            }
+            int nloc = 0;
+            bool reached = false;
+            for (;;) {
+                bool work = valid && status == SB_SUCCESS && !reached;
+                if (work && !bdf.in_step) {
+                    if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                    else status = bdf.pre_step_checks();
+                    work = status == SB_SUCCESS;
                 }
-                if (status != SB_SUCCESS) break;
+                if (!sb_any(work)) break;
+                if (work) {
+                    const int r = bdf.attempt(sys);
+                    if (r == SB_SUCCESS) {
+                        nloc++;
+                        bdf.snap_to_tstop();
+                        if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
+                        else bdf.limit_to_tstop();
+                    } else if (r != SB_TRY_AGAIN) {
+                        status = r;
+                    }
+                }
+            }
+            if (valid && status == SB_SUCCESS) {
                 bdf.get_dky(t_lower, lam);                // CVodeGetB
                 if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
             }
-            if (k < a.n_t) {
-                const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
+        }
+        if (k < a.n_t) {
+            const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) lam[i] -= g[i];
-            }
+            for (int i = 0; i < NS; ++i) lam[i] -= g[i];
         }
     }
+    if (!valid) return;
     if (status != SB_SUCCESS) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) lam[i] = qnan();
@@ -297,7 +348,7 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const SbForwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst < a.B) sb::forward_instance(a, inst);
+    sb::forward_instance(a, inst, inst < a.B);
 }
 
 extern "C" __global__ void __launch_bounds__(256)
@@ -311,7 +362,7 @@ sb_tables(const SbTablesArgs a) {
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_backward(const SbBackwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst < a.B) sb::backward_instance(a, inst);
+    sb::backward_instance(a, inst, inst < a.B);
 }
 
 extern "C" __global__ void __launch_bounds__(256)

@@ -1,4 +1,5 @@
 // Entry points of the host emulation build: loop over instances instead of launching a grid.
+#define SB_HOST_EMULATION 1
 #include "cuda_shim.h"
 #include "generated_problem.inc"     // generated __device__ functions + SB_NS/SB_NP/SB_ND
 #include "sb_kernels.cuh"
@@ -6,7 +7,7 @@
 extern "C" {
 void emu_forward(const SbForwardArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
-    for (long long i = 0; i < a->B; ++i) sb::forward_instance(*a, i);
+    for (long long i = 0; i < a->B; ++i) sb::forward_instance(*a, i, true);
 }
 void emu_tables(const SbTablesArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
@@ -15,7 +16,7 @@ void emu_tables(const SbTablesArgs* a) {
 }
 void emu_backward(const SbBackwardArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
-    for (long long i = 0; i < a->B; ++i) sb::backward_instance(*a, i);
+    for (long long i = 0; i < a->B; ++i) sb::backward_instance(*a, i, true);
 }
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
 }

@@ -1,0 +1,38 @@
+"""Problem definitions shared by the golden-vector generator (which feeds them to the REFERENCE's
+SympyProblem) and the tests (which feed them to ours).  name -> (params, states, rhs, deriv)."""
+import numpy as np
+import sympy as sym
+
+
+def _lv(t, y, p):
+    return {'hares': p.alpha * y.hares - p.beta * y.lynx * y.hares,
+            'lynx': p.delta * y.hares * y.lynx - p.gamma * y.lynx}
+
+
+def _robertson(t, y, p):
+    return {'y1': -p.k1 * y.y1 + p.k3 * y.y2 * y.y3,
+            'y2': p.k1 * y.y1 - p.k3 * y.y2 * y.y3 - p.k2 * y.y2 ** 2,
+            'y3': p.k2 * y.y2 ** 2}
+
+
+def _nested(t, y, p):
+    # nested params/states, a vector state, time dependence and transcendental functions
+    return {
+        'a': p.c.d * y.a + p.f[2] * sym.sin(t),
+        'b': {'c': [3. * sym.exp(-y.b.c[1]), 4. * y.a[0] / (1 + y.b.c[0] ** 2)]},
+    }
+
+
+def _one_fixed(t, y, p):
+    # derivative wrt the second parameter only; the first one is a "remaining" parameter
+    return {'x': p.r * y.x * (1 - y.x / p.K) + sym.sqrt(y.x)}
+
+
+CASES = {
+    'lv': ({'alpha': (), 'beta': (), 'gamma': (), 'delta': ()}, {'hares': (), 'lynx': ()}, _lv,
+           [('alpha',), ('beta',)]),
+    'robertson': ({'k1': (), 'k2': (), 'k3': ()}, {'y1': (), 'y2': (), 'y3': ()}, _robertson,
+                  [('k1',), ('k2',), ('k3',)]),
+    'nested': ({'c': {'d': 3}, 'f': 4}, {'a': 3, 'b': {'c': 2}}, _nested, [('c', 'd')]),
+    'one_fixed': ({'r': (), 'K': ()}, {'x': ()}, _one_fixed, [('K',)]),
+}
