@@ -47,8 +47,12 @@ def compile_cubin(gen: GeneratedSource, *, arch: str = DEFAULT_ARCH,
     configuration."""
     block = int(block_threads or DEFAULT_BLOCK)
     minb = int(min_blocks or DEFAULT_MIN_BLOCKS)
-    path = os.path.join(cache_dir(), 'k_%s_%s_%s_b%d_m%d.cubin'
-                        % (gen.digest, kernel_source_hash(), arch, block, minb))
+    # kernel build variants for A/B measurements: SUNODE_B200_DEFINES="SB_INLINE_MATH,SB_FOO=2"
+    defines = [d.strip() for d in os.environ.get('SUNODE_B200_DEFINES', '').split(',') if d.strip()]
+    prelude = ''.join('#define %s\n' % d.replace('=', ' ', 1) for d in defines)
+    tag = ('_' + hashlib.sha256(prelude.encode()).hexdigest()[:8]) if prelude else ''
+    path = os.path.join(cache_dir(), 'k_%s_%s_%s_b%d_m%d%s.cubin'
+                        % (gen.digest, kernel_source_hash(), arch, block, minb, tag))
     if use_cache and os.path.exists(path):
         with open(path, 'rb') as fh:
             return fh.read(), path
@@ -56,7 +60,7 @@ def compile_cubin(gen: GeneratedSource, *, arch: str = DEFAULT_ARCH,
     cubin = ctypes.c_void_p()
     size = ctypes.c_size_t(0)
     log = ctypes.c_void_p()
-    code = lib.sb_compile(gen.cuda.encode(), arch.encode(), block, minb, ctypes.byref(cubin),
+    code = lib.sb_compile((prelude + gen.cuda).encode(), arch.encode(), block, minb, ctypes.byref(cubin),
                           ctypes.byref(size), ctypes.byref(log))
     log_text = ''
     if log.value:

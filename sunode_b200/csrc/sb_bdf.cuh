@@ -66,6 +66,43 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 #define SB_IDX(J) decltype(J)::value
 
+// Division, square root and the controller's k-th roots are the bulky pieces of double-precision
+// code (each inlined division is ~18 instructions with its slow path, and there are dozens per
+// step).  The integrator is instruction-cache bound (ncu: a third of all stalls are `no_inst`), so
+// they are single out-of-line copies by default; -DSB_INLINE_MATH restores inlining for A/B runs.
+#if defined(SB_HOST_EMULATION) || defined(SB_INLINE_MATH)
+#define SB_MATH_FN __device__ __forceinline__
+#else
+#define SB_MATH_FN __device__ __noinline__
+#endif
+SB_MATH_FN double sb_div(double a, double b) { return a / b; }
+SB_MATH_FN double sb_sqrt(double a) { return sqrt(a); }
+
+// x^(1/k), k = 1..7, for the step-size controller (CVODES: SUNRpowerR(x, 1/k)).  k = 2, 3, 4, 6
+// reduce to sqrt / cbrt; k = 5, 7 take two Newton steps on y^k = x from a single-precision seed.
+// All variants are good to an ulp or two, the same as pow().
+SB_MATH_FN double root_k(double x, int k) {
+    if (k == 1) return x;
+    if (k == 2) return sqrt(x);
+    if (k == 4) return sqrt(sqrt(x));
+    if (k == 3) return cbrt(x);
+    if (k == 6) return cbrt(sqrt(x));
+    if (!(x > 1e-30 && x < 1e30)) return pow(x, 1.0 / (double)k);   // 0, inf, nan, extreme: rare
+#ifdef SB_HOST_EMULATION
+    double y = (double)powf((float)x, 1.0f / (float)k);
+#else
+    double y = (double)exp2f(__log2f((float)x) * (1.0f / (float)k));
+#endif
+    const double rk = 1.0 / (double)k, km1 = (double)(k - 1);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y, y4 = y2 * y2;
+        const double yk = (k == 5) ? y4 * y : y4 * y2 * y;
+        y = y * (km1 + x / yk) * rk;
+    }
+    return y;
+}
+
 template <int N>
 __device__ __forceinline__ bool all_finite(const double* v) {
     double s = 0.0;
@@ -79,11 +116,8 @@ __device__ __forceinline__ double wrms(const double* v, const double* w) {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) { const double x = v[i] * w[i]; s = fma(x, x, s); }
-    return sqrt(s * (1.0 / N));
+    return sb_sqrt(s * (1.0 / N));
 }
-
-// x^(1/k) for the step-size controller
-__device__ __forceinline__ double root_k(double x, int k) { return pow(x, 1.0 / (double)k); }
 
 // ---- dense LU with partial pivoting, fully unrolled, rows swapped physically -----------------
 // a is column-major a[i + N*j].  The row permutation is recorded as N small ints.
@@ -112,7 +146,7 @@ __device__ __forceinline__ bool lu_factor(double* a, int* piv) {
                 a[i + N * j] = sw ? u : v;
             }
         });
-        const double mult = 1.0 / a[k + N * k];
+        const double mult = sb_div(1.0, a[k + N * k]);
 #pragma unroll
         for (int i = k + 1; i < N; ++i) a[i + N * k] *= mult;
 #pragma unroll
@@ -144,7 +178,7 @@ __device__ __forceinline__ void lu_solve(const double* a, const int* piv, double
         for (int i = k + 1; i < N; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        b[k] /= a[k + N * k];
+        b[k] = sb_div(b[k], a[k + N * k]);
 #pragma unroll
         for (int i = 0; i < k; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
     }
@@ -183,6 +217,11 @@ struct Bdf {
     double step_t0;
     int ncf, nef, nefQ, nflag;
     bool in_step;
+    // History manipulations requested by the previous pass (failed pass: restore + rescale, maybe
+    // an order drop; new step with a new step size: rescale, maybe an order change).  They are
+    // carried out at ONE place, the top of the next attempt(), so that the bulky restore /
+    // rescale / order-change code exists once instead of once per failure branch.
+    int pend;
 
     // ------------------------------------------------------------------ (re)initialisation
     // CVodeReInit (+ CVodeQuadReInit): order 1, fresh controller state, counters cleared
@@ -206,7 +245,7 @@ struct Bdf {
         saved_tq5 = 0.0; jcur = false; crate = 1.0; delp = 0.0; acnrm = 0.0;
         tstopset = false; tstop = 0.0;
         h = hprime = hscale = 0.0; eta = 1.0; gamma = gammap = gamrat = 1.0; rl1 = 1.0;
-        in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL;
+        in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL; pend = 0;
     }
 
     __device__ __forceinline__ void clear_stats() {
@@ -219,14 +258,14 @@ struct Bdf {
         for (int i = 0; i < N; ++i) {
             const double d = fma(reltol, fabs(zn[0][i]), abstol[i]);
             ok = ok && (d > 0.0);
-            ewt[i] = 1.0 / d;
+            ewt[i] = sb_div(1.0, d);
         }
         if (QUAD) {
 #pragma unroll
             for (int i = 0; i < NQ_; ++i) {
                 const double d = fma(reltolQ, fabs(znQ[0][i]), abstolQ);
                 ok = ok && (d > 0.0);
-                ewtQ[i] = 1.0 / d;
+                ewtQ[i] = sb_div(1.0, d);
             }
         }
         return ok;
@@ -396,17 +435,17 @@ struct Bdf {
         for (int j = 1; j < SB_QMAX; ++j) {
             if (j < q) {
                 hsum += tau[j + 1];
-                const double xi = hsum / hscale;
+                const double xi = sb_div(hsum, hscale);
                 prod *= xi;
                 alpha0 -= 1.0 / (double)(j + 1);
-                alpha1 += 1.0 / xi;
+                alpha1 += sb_div(1.0, xi);
 #pragma unroll
                 for (int i = SB_LMAX - 1; i >= 2; --i)
                     if (i <= j + 2) lc[i] = fma(lc[i], xiold, lc[i - 1]);
                 xiold = xi;
             }
         }
-        const double A1 = (-alpha0 - alpha1) / prod;
+        const double A1 = sb_div(-alpha0 - alpha1, prod);
         double znew[N], znewQ[NQ_];
 #pragma unroll
         for (int i = 0; i < N; ++i) znew[i] = A1 * zsave[i];
@@ -444,7 +483,7 @@ struct Bdf {
         for (int j = 1; j <= SB_QMAX - 2; ++j) {
             if (j <= q - 2) {
                 hsum += tau[j];
-                const double xi = hsum / hscale;
+                const double xi = sb_div(hsum, hscale);
 #pragma unroll
                 for (int i = SB_LMAX - 1; i >= 2; --i)
                     if (i <= j + 2) lc[i] = fma(lc[i], xi, lc[i - 1]);
@@ -494,13 +533,38 @@ struct Bdf {
         }
     }
 
-    __device__ __forceinline__ void adjust_params() {
-        if (qprime != q) {
+    static constexpr int PEND_RESTORE = 1, PEND_ORDER = 2, PEND_RESCALE = 4, PEND_RELOAD = 8;
+
+    // cvAdjustParams / the tails of cvHandleNFlag and cvDoErrorTest, in their original order:
+    // restore, order change (towards qprime), rescale by eta; or the order-1 reload.
+    __device__ __forceinline__ int apply_pending(Sys& sys) {
+        if (pend & PEND_RESTORE) restore(step_t0);
+        if (pend & PEND_ORDER) {
             if (qprime > q) increase_order();
             else drop_order();
             q = qprime; L = q + 1; qwait = L;
         }
-        rescale();
+        if (pend & PEND_RESCALE) rescale();
+        int ret = SB_SUCCESS;
+        if (pend & PEND_RELOAD) {
+            // order 1 and still failing: reload the first derivative from scratch
+            h *= eta; hscale = h; qwait = LONG_WAIT;
+            double f[N];
+            sys.set_time(tn);
+            sys.rhs(zn[0], f); st.nfe++;
+            if (!all_finite<N>(f)) ret = SB_UNREC_RHSFUNC_ERR;
+#pragma unroll
+            for (int i = 0; i < N; ++i) zn[1][i] = h * f[i];
+            if (QUAD) {
+                double fq[NQ_];
+                sys.quad(zn[0], fq);
+                if (!all_finite<NQ_>(fq)) ret = SB_RHSFUNC_FAIL;
+#pragma unroll
+                for (int i = 0; i < NQ_; ++i) znQ[1][i] = h * fq[i];
+            }
+        }
+        pend = 0;
+        return ret;
     }
 
     // ------------------------------------------------------------------ cvSetBDF + cvSetTqBDF
@@ -514,7 +578,7 @@ struct Bdf {
             for (int j = 2; j < SB_QMAX; ++j) {
                 if (j < q) {
                     hsum += tau[j - 1];
-                    xi_inv = h / hsum;
+                    xi_inv = sb_div(h, hsum);
                     alpha0 -= 1.0 / (double)j;
 #pragma unroll
                     for (int i = SB_QMAX; i >= 1; --i)
@@ -529,7 +593,7 @@ struct Bdf {
                 tau_qm1 = (j == q - 1) ? tau[j] : tau_qm1;
             });
             hsum += tau_qm1;
-            xi_inv = h / hsum;
+            xi_inv = sb_div(h, hsum);
             alpha0_hat = -l[1] - xi_inv;
 #pragma unroll
             for (int i = SB_QMAX; i >= 1; --i)
@@ -543,34 +607,34 @@ struct Bdf {
         });
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        tq[2] = fabs(A1 / (alpha0 * A2));
-        tq[5] = fabs(A2 * xistar_inv / (lq * xi_inv));
+        tq[2] = fabs(sb_div(A1, alpha0 * A2));
+        tq[5] = fabs(sb_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
-                const double C = xistar_inv / lq;
+                const double C = sb_div(xistar_inv, lq);
                 const double A3 = alpha0 + 1.0 / (double)q;
                 const double A4 = alpha0_hat + xi_inv;
-                const double Cpinv = (1.0 - A4 + A3) / A3;
+                const double Cpinv = sb_div(1.0 - A4 + A3, A3);
                 tq[1] = fabs(C * Cpinv);
             } else tq[1] = 1.0;
             hsum += tau_q;
-            xi_inv = h / hsum;
+            xi_inv = sb_div(h, hsum);
             const double A5 = alpha0 - (1.0 / (double)(q + 1));
             const double A6 = alpha0_hat - xi_inv;
-            const double Cppinv = (1.0 - A6 + A5) / A2;
-            tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+            const double Cppinv = sb_div(1.0 - A6 + A5, A2);
+            tq[3] = fabs(sb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq[4] = NLSCOEF / tq[2];
-        rl1 = 1.0 / l[1];
+        tq[4] = sb_div(NLSCOEF, tq[2]);
+        rl1 = sb_div(1.0, l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
-        gamrat = (nst > 0) ? gamma / gammap : 1.0;
+        gamrat = (nst > 0) ? sb_div(gamma, gammap) : 1.0;
     }
 
     // ------------------------------------------------------------------ linear setup
     // returns 0 ok, 1 recoverable
     __device__ __forceinline__ int lsetup(Sys& sys, int convfail, const double* ypred) {
-        const double dgamma = fabs(gamma / gammap - 1.0);
+        const double dgamma = fabs(sb_div(gamma, gammap) - 1.0);
         const bool jbad = (nst == 0) || (nst > nstlj + MSBJ) ||
                           (convfail == FAIL_BAD_J && dgamma < LS_DGMAX) || (convfail == FAIL_OTHER);
         if (jbad) {
@@ -617,15 +681,15 @@ struct Bdf {
                     st.nni++;
                     lu_solve<N>(M, piv, delta);
                     if (gamrat != 1.0) {
-                        const double s = 2.0 / (1.0 + gamrat);
+                        const double s = sb_div(2.0, 1.0 + gamrat);
 #pragma unroll
                         for (int i = 0; i < N; ++i) delta[i] *= s;
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) { acor[i] += delta[i]; ycur[i] = zn[0][i] + acor[i]; }
                     const double del = wrms<N>(delta, ewt);
-                    if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
-                    const double dcon = del * fmin(1.0, crate) / tq[4];
+                    if (m > 0) crate = fmax(CRDOWN * crate, sb_div(del, delp));
+                    const double dcon = sb_div(del * fmin(1.0, crate), tq[4]);
                     if (dcon <= 1.0) {
                         acnrm = (m == 0) ? del : wrms<N>(acor, ewt);
                         jcur = false;
@@ -693,7 +757,7 @@ struct Bdf {
             qprime = q; hprime = h; eta = 1.0;
             return;
         }
-        const double etaq = 1.0 / (root_k(BIAS2 * dsm, L) + ADDON);
+        const double etaq = sb_div(1.0, root_k(BIAS2 * dsm, L) + ADDON);
         if (qwait != 0) { eta = etaq; qprime = q; set_eta(); return; }
         qwait = 2;
         double etaqm1 = 0.0, etaqp1 = 0.0;
@@ -714,14 +778,14 @@ struct Bdf {
             double ddn = wrms<N>(zq, ewt);
             if (QUAD) ddn = fmax(ddn, wrms<NQ_>(zqQ, ewtQ));
             ddn *= tq[1];
-            etaqm1 = 1.0 / (root_k(BIAS1 * ddn, q) + ADDON);
+            etaqm1 = sb_div(1.0, root_k(BIAS1 * ddn, q) + ADDON);
         }
         if (q != SB_QMAX && saved_tq5 != 0.0) {
-            const double r = h / tau[2];
+            const double r = sb_div(h, tau[2]);
             double rp = r;
 #pragma unroll
             for (int j = 2; j <= SB_LMAX; ++j) if (j <= L) rp *= r;
-            const double cquot = (tq[5] / saved_tq5) * rp;
+            const double cquot = sb_div(tq[5], saved_tq5) * rp;
             double tmp[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) tmp[i] = fma(-cquot, zsave[i], acor[i]);
@@ -733,7 +797,7 @@ struct Bdf {
                 dup = fmax(dup, wrms<NQ_>(tmpq, ewtQ));
             }
             dup *= tq[3];
-            etaqp1 = 1.0 / (root_k(BIAS3 * dup, L + 1) + ADDON);
+            etaqp1 = sb_div(1.0, root_k(BIAS3 * dup, L + 1) + ADDON);
         }
         const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
         if (etam < THRESH) { eta = 1.0; qprime = q; }
@@ -751,42 +815,27 @@ struct Bdf {
         set_eta();
     }
 
-    // Shared tail of a failed error test (cvDoErrorTest after the `dsm > 1` branch).
+    // Tail of a failed error test (cvDoErrorTest after the `dsm > 1` branch): decides how the
+    // step is retried; the history manipulation itself is queued in `pend`.
     // returns 0 = try again, <0 = fatal
-    __device__ __forceinline__ int error_test_failed(Sys& sys, double saved_t, double dsm, int nef) {
+    __device__ __forceinline__ int error_test_failed(double dsm, int nef_) {
         st.netf++;
-        restore(saved_t);
-        if (nef == MXNEF) return SB_ERR_FAILURE;
+        pend = PEND_RESTORE;
+        if (nef_ == MXNEF) return SB_ERR_FAILURE;
         etamax = 1.0;
-        if (nef <= MXNEF1) {
-            eta = 1.0 / (root_k(BIAS2 * dsm, L) + ADDON);
+        if (nef_ <= MXNEF1) {
+            eta = sb_div(1.0, root_k(BIAS2 * dsm, L) + ADDON);
             eta = fmax(ETAMIN, eta);
-            if (nef >= SMALL_NEF) eta = fmin(eta, ETAMXF);
-            rescale();
+            if (nef_ >= SMALL_NEF) eta = fmin(eta, ETAMXF);
+            pend |= PEND_RESCALE;
             return 0;
         }
-        if (q > 1) {
-            eta = ETAMIN;
-            drop_order();
-            L = q; q--; qwait = L;
-            rescale();
-            return 0;
-        }
-        // order 1: reload the first derivative from scratch
         eta = ETAMIN;
-        h *= eta; hscale = h; qwait = LONG_WAIT;
-        double f[N];
-        sys.set_time(tn);
-        sys.rhs(zn[0], f); st.nfe++;
-        if (!all_finite<N>(f)) return SB_UNREC_RHSFUNC_ERR;
-#pragma unroll
-        for (int i = 0; i < N; ++i) zn[1][i] = h * f[i];
-        if (QUAD) {
-            double fq[NQ_];
-            sys.quad(zn[0], fq);
-            if (!all_finite<NQ_>(fq)) return SB_RHSFUNC_FAIL;
-#pragma unroll
-            for (int i = 0; i < NQ_; ++i) znQ[1][i] = h * fq[i];
+        if (q > 1) {
+            qprime = q - 1;                 // cvAdjustOrder(-1); L = q; q--; qwait = L
+            pend |= PEND_ORDER | PEND_RESCALE;
+        } else {
+            pend |= PEND_RELOAD;
         }
         return 0;
     }
@@ -799,27 +848,31 @@ struct Bdf {
         if (!in_step) {
             step_t0 = tn;
             ncf = 0; nef = 0; nefQ = 0; nflag = FIRST_CALL;
-            if (nst > 0 && hprime != h) adjust_params();
+            pend = 0;
+            if (nst > 0 && hprime != h) pend = PEND_RESCALE | ((qprime != q) ? PEND_ORDER : 0);
             in_step = true;
+        }
+        if (pend != 0) {
+            const int pr = apply_pending(sys);
+            if (pr != SB_SUCCESS) { in_step = false; return pr; }
         }
         predict();
         set_coeffs();
         const int nr = nls(sys, nflag);
         if (nr != 0) {
             st.ncfn++; ncf++;
-            restore(step_t0);
             etamax = 1.0;
             if (ncf == MXNCF) { in_step = false; return SB_CONV_FAILURE; }
             eta = ETACF;
             nflag = PREV_CONV_FAIL;
-            rescale();
+            pend = PEND_RESTORE | PEND_RESCALE;
             return SB_TRY_AGAIN;
         }
         double dsm = acnrm * tq[2];
         if (!(dsm <= 1.0)) {
             nef++;
             nflag = PREV_ERR_FAIL;
-            const int r = error_test_failed(sys, step_t0, dsm, nef);
+            const int r = error_test_failed(dsm, nef);
             if (r < 0) { in_step = false; return r; }
             return SB_TRY_AGAIN;
         }
@@ -829,12 +882,11 @@ struct Bdf {
             sys.quad(ycur, fq);
             if (!all_finite<NQ_>(fq)) {
                 st.ncfn++; ncf++;
-                restore(step_t0);
                 etamax = 1.0;
                 if (ncf == MXNCF) { in_step = false; return SB_REPTD_RHSFUNC_ERR; }
                 eta = ETACF;
                 nflag = PREV_CONV_FAIL;
-                rescale();
+                pend = PEND_RESTORE | PEND_RESCALE;
                 return SB_TRY_AGAIN;
             }
 #pragma unroll
@@ -843,7 +895,7 @@ struct Bdf {
             if (!(dsmQ <= 1.0)) {
                 nefQ++;
                 nflag = PREV_ERR_FAIL;
-                const int r = error_test_failed(sys, step_t0, dsmQ, nefQ);
+                const int r = error_test_failed(dsmQ, nefQ);
                 if (r < 0) { in_step = false; return r; }
                 return SB_TRY_AGAIN;
             }
@@ -866,7 +918,7 @@ struct Bdf {
 
     // ------------------------------------------------------------------ dense output
     __device__ __forceinline__ void get_dky(double t, double* out) const {
-        const double s = (t - tn) / h;
+        const double s = sb_div(t - tn, h);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double acc = 0.0;
@@ -877,7 +929,7 @@ struct Bdf {
     }
 
     __device__ __forceinline__ void get_quad(double t, double* out) const {
-        const double s = (t - tn) / h;
+        const double s = sb_div(t - tn, h);
 #pragma unroll
         for (int i = 0; i < NQ_; ++i) {
             double acc = 0.0;
@@ -907,7 +959,7 @@ struct Bdf {
     __device__ __forceinline__ void limit_to_tstop() {
         if (tstopset && (tn + hprime - tstop) * h > 0.0) {
             hprime = (tstop - tn) * (1.0 - 4.0 * SB_UROUND);
-            eta = hprime / h;
+            eta = sb_div(hprime, h);
         }
     }
 };

@@ -96,8 +96,9 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
 
     for (;;) {
         bool work = valid && status == SB_SUCCESS && k < a.n_t;
-        if (work) {
-            // emit the output times that need no further step
+        if (work && !bdf.in_step) {
+            // emit the output times that need no further step (never in the middle of a step:
+            // a failed pass leaves the history un-restored until the next attempt)
             for (;;) {
                 const double tout = a.tvals[k];
                 if (tout == a.t0) {

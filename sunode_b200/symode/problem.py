@@ -253,6 +253,10 @@ class SympyProblem(Problem):
         state = dict(self.__dict__)
         state['_host'] = None
         state['_simplify'] = None
+        # attribute trees of symbols: dynamically created dataclasses, only needed while the
+        # user's rhs is being traced in __init__
+        state['_sym_params'] = None
+        state['_sym_states'] = None
         return state
 
     def __setstate__(self, state):

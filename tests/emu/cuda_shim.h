@@ -16,7 +16,7 @@
 #define __restrict__
 
 using std::fma; using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::pow;
-using std::max; using std::min; using std::exp; using std::log; using std::log1p;
+using std::max; using std::min; using std::exp; using std::log; using std::log1p; using std::cbrt;
 
 static inline double __ldg(const double* p) { return *p; }
 static inline int __ldg(const int* p) { return *p; }

@@ -1,0 +1,70 @@
+"""CPU tier: the DEVICE integrator sources (csrc/sb_bdf.cuh, sb_kernels.cuh + the generated
+__device__ functions) compiled for the host by tests/emu and compared with the oracle.  This
+checks the kernel logic where no GPU is available; the `-m gpu` tier runs the same comparison on
+the real kernels through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from sunode_b200 import examples
+from tests.emu.emu import Emulator
+
+
+@pytest.mark.parametrize('name,env', [('lv_adj', 1e-3), ('seir_adj', 1e-3), ('robertson_adj', 1000.0)])
+def test_device_logic_matches_oracle(name, env, tmp_path):
+    w = examples.workloads()[name]
+    prob = w.make_problem()
+    B = 48
+    y0, theta = w.draws(B)
+    grads = np.random.default_rng(11).standard_normal((B, len(w.tvals), prob.n_states))
+    emu = Emulator(prob, str(tmp_path))
+    r = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity)
+    yo, go, lo, so, sto = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(
+        w.t0, w.tvals, y0, theta, grads)
+    assert (r['status'] == 0).all() and (so == 0).all()
+    tol = 1e-8 * np.abs(yo) + 1e-8
+    assert np.max(np.abs(r['y'] - yo) / tol) <= env
+    gtol = 1e-9 if env < 1 else 1e-5
+    assert np.max(np.abs(r['grad'] - go) / np.abs(go).max(axis=0)) <= gtol
+    assert np.max(np.abs(r['lamda'] - lo) / np.abs(lo).max(axis=0)) <= max(gtol, 1e-4 if env > 1 else 0)
+    if env < 1:
+        np.testing.assert_array_equal(r['fwd']['stats'][:, 0], sto[:, 0])     # same step sequence
+        np.testing.assert_array_equal(r['stats'][:, 0], sto[:, 7])
+
+
+def test_history_and_tables_reproduce_forward_solution(tmp_path):
+    """The interpolation tables built from the stored steps (sb_tables) evaluate to the stored
+    points at the step times, and the stored history equals the oracle's data points."""
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(1)
+    emu = Emulator(prob, str(tmp_path))
+    r = emu.adjoint(w.t0, w.tvals, y0, theta, np.ones((50, 2)), 1e-8, 1e-8, hist_cap=512)
+    n = r['fwd']['hist_n'][0]
+    hist = r['fwd']['hist'][0, :n]
+    st, _, ht, ho, hy = Oracle(prob, rtol=1e-8, atol=1e-8).forward_history(
+        w.t0, w.tvals, y0, theta)
+    assert st == 0 and len(ht) == n
+    # same step sequence; the step sizes agree to rounding-error propagation (the device code
+    # uses explicit FMAs, the oracle plain arithmetic)
+    np.testing.assert_allclose(hist[:, 0], ht, rtol=1e-8)
+    np.testing.assert_array_equal(hist[1:, 1].astype(int), ho[1:])
+    np.testing.assert_allclose(hist[:, 2:], hy, rtol=1e-8)
+    tab = r['tab'][0]
+    for idx in range(1, n):
+        e = tab[idx]
+        assert e[0] == hist[idx - 1, 0] and e[1] == hist[idx, 0]
+        np.testing.assert_array_equal(e[10:12], hist[idx, 2:])               # Y[0] = right end point
+
+
+def test_tolerance_mxstep_and_capacity_limits(tmp_path):
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(4)
+    emu = Emulator(prob, str(tmp_path))
+    r = emu.forward(w.t0, w.tvals, y0, theta, 1e-8, 1e-8, max_steps=1)       # 1 step per tval
+    assert (r['status'] == -1).all() and np.isnan(r['y']).all()              # CV_TOO_MUCH_WORK
+    r = emu.forward(w.t0, w.tvals, y0, theta, 1e-8, 1e-8, hist_cap=16, max_steps=2500)
+    assert (r['status'] == -1).all()                                         # history overflow
+    r = emu.forward(w.t0, w.tvals, y0, theta, 0.0, 0.0)                      # ewt undefined
+    assert (r['status'] == -22).all()                                        # CV_ILL_INPUT

@@ -136,12 +136,12 @@ def test_adjoint_gradient_against_finite_differences(name):
     assert np.max(np.abs(grad[0] - fd)) <= 2e-5 * scale, (grad[0], fd)
     fd0 = np.zeros(prob.n_states)
     for j in range(prob.n_states):
-        h = 1e-6 * max(abs(y0[0, j]), 1e-2)
+        h = 1e-6 * abs(y0[0, j]) if y0[0, j] != 0 else 1e-7
         yp, ym = y0.copy(), y0.copy()
         yp[0, j] += h
         ym[0, j] -= h
         fd0[j] = (loss(theta, yp) - loss(theta, ym)) / (2 * h)
-    assert np.max(np.abs(-lam[0] - fd0)) <= 1e-4 * np.max(np.abs(fd0)), (-lam[0], fd0)
+    assert np.max(np.abs(-lam[0] - fd0)) <= 2e-4 * np.max(np.abs(fd0)), (-lam[0], fd0)
 
 
 def test_failure_codes_and_nan_fill():
