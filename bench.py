@@ -119,7 +119,7 @@ def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8)
     y0, theta = w.draws(n_sample)
-    grads = np.ones((len(w.tvals), problem.n_states))
+    grads = w.grads(problem.n_states)
     cores = threads or max_threads()
     best = None
     for _ in range(repeats):
@@ -140,7 +140,7 @@ def run_reference(args, w, problem, rank, world):
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8)
     y0, theta = w.draws(n_sample)
-    grads = np.ones((len(w.tvals), problem.n_states))
+    grads = w.grads(problem.n_states)
     cores = max_threads()
 
     def step():
@@ -183,7 +183,8 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
         'batch_per_gpu': int(batch), 'global_batch': int(batch) * n_gpus,
         'rtol': 1e-8, 'atol': 1e-8, 'rtol_backward': 1e-10, 'atol_backward': 1e-10,
         'method': 'BDF(1-5) + Newton/dense LU; adjoint: backward BDF restarted at every tval + quadrature',
-        'cotangent': 'ones((n_t, n_s)) shared by all instances',
+        'cotangent': ('ones((n_t, n_s))' if w.cotangent == 'ones' else 'seeded N(0,1) [n_t, n_s]')
+                     + ' shared by all instances',
         'theta': 'theta_med * exp(%g * N(0,1)), seed %d' % (w.sigma, w.seed),
         'parallelism': 'dp%d (independent draws, contiguous shards)' % n_gpus,
     }
@@ -220,7 +221,7 @@ def main():
     B = args.batch or w.batch
     n_t, n_s, n_all, n_d = len(w.tvals), problem.n_states, problem.n_params_total, problem.n_params
     y0_h, theta_h = w.draws(B, offset=rank * B)
-    grads_h = np.ones((n_t, n_s))
+    grads_h = w.grads(n_s)
     if w.adjoint:
         solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8,
                                history_capacity=w.history_capacity, device=local_rank,

@@ -66,41 +66,73 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 #define SB_IDX(J) decltype(J)::value
 
-// Division, square root and the controller's k-th roots are the bulky pieces of double-precision
-// code (each inlined division is ~18 instructions with its slow path, and there are dozens per
-// step).  The integrator is instruction-cache bound (ncu: a third of all stalls are `no_inst`), so
-// they are single out-of-line copies by default; -DSB_INLINE_MATH restores inlining for A/B runs.
-#if defined(SB_HOST_EMULATION) || defined(SB_INLINE_MATH)
-#define SB_MATH_FN __device__ __forceinline__
+// Division, square root and the controller's k-th roots.  The compiler's IEEE sequences for these
+// carry a special-case slow path each (~18-27 instructions per division with the call); with
+// dozens of divisions per step they were a third of all executed instructions and blew the
+// instruction cache (ncu: `no_inst` was a third of all stalls).  The integrator's operands are
+// well-scaled normal numbers, so it uses branch-free Newton sequences seeded by the SFU
+// approximations instead: results are within an ulp of the IEEE ones.  -DSB_EXACT_MATH restores
+// the IEEE operations (out of line, to keep the code small).
+#if defined(SB_HOST_EMULATION)
+__device__ __forceinline__ double sb_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double sb_sqrt(double a) { return sqrt(a); }
+#elif defined(SB_EXACT_MATH)
+__device__ __noinline__ double sb_div(double a, double b) { return a / b; }
+__device__ __noinline__ double sb_sqrt(double a) { return sqrt(a); }
 #else
-#define SB_MATH_FN __device__ __noinline__
+__device__ __forceinline__ double sb_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));      // MUFU.RCP64H: ~20 good bits
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);                                           // 1/b to ~1 ulp
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);                            // residual correction
+}
+__device__ __forceinline__ double sb_sqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));    // MUFU.RSQ64H
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    r = fma(r, fma(-hx * r, r, 0.5), r);                        // 1/sqrt(x) to ~1 ulp
+    const double s = x * r;
+    const double y = fma(fma(-s, s, x), 0.5 * r, s);
+    return (x > 0.0) ? y : x;                                   // 0 -> 0, nan -> nan (norms are >= 0)
+}
 #endif
-SB_MATH_FN double sb_div(double a, double b) { return a / b; }
-SB_MATH_FN double sb_sqrt(double a) { return sqrt(a); }
 
-// x^(1/k), k = 1..7, for the step-size controller (CVODES: SUNRpowerR(x, 1/k)).  k = 2, 3, 4, 6
-// reduce to sqrt / cbrt; k = 5, 7 take two Newton steps on y^k = x from a single-precision seed.
-// All variants are good to an ulp or two, the same as pow().
-SB_MATH_FN double root_k(double x, int k) {
-    if (k == 1) return x;
-    if (k == 2) return sqrt(x);
-    if (k == 4) return sqrt(sqrt(x));
-    if (k == 3) return cbrt(x);
-    if (k == 6) return cbrt(sqrt(x));
-    if (!(x > 1e-30 && x < 1e30)) return pow(x, 1.0 / (double)k);   // 0, inf, nan, extreme: rare
+// x^(1/k), k = 2..7, for the step-size controller (CVODES: SUNRpowerR(x, 1/k)).  One branch-free
+// sequence for every k: z ~ x^(-1/k) from the single-precision SFU log2/exp2, two division-free
+// Newton steps z <- z (1 + (1 - x z^k) / k), then x^(1/k) = x z^(k-1).  Good to a few ulp, like
+// pow(), at a quarter of its instructions; out of line because it has four call sites.
 #ifdef SB_HOST_EMULATION
-    double y = (double)powf((float)x, 1.0f / (float)k);
+static const double sb_rk_table[8] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7};
+#define SB_ROOT_FN inline
 #else
-    double y = (double)exp2f(__log2f((float)x) * (1.0f / (float)k));
+__constant__ double sb_rk_table[8] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7};
+#define SB_ROOT_FN __device__ __noinline__
 #endif
-    const double rk = 1.0 / (double)k, km1 = (double)(k - 1);
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double y2 = y * y, y4 = y2 * y2;
-        const double yk = (k == 5) ? y4 * y : y4 * y2 * y;
-        y = y * (km1 + x / yk) * rk;
-    }
-    return y;
+__device__ __forceinline__ double sb_ipow(double z, int k) {   // z^k, 0 <= k <= 7
+    const double z2 = z * z, z4 = z2 * z2;
+    return ((k & 1) ? z : 1.0) * ((k & 2) ? z2 : 1.0) * ((k & 4) ? z4 : 1.0);
+}
+SB_ROOT_FN double root_k(double x, int k) {
+    if (k == 1) return x;
+#ifdef SB_EXACT_MATH
+    return pow(x, 1.0 / (double)k);
+#else
+    if (!(x > 1e-30 && x < 1e30)) return pow(x, 1.0 / (double)k);   // 0, inf, nan, extreme: rare
+    const double rk = sb_rk_table[k];
+#ifdef SB_HOST_EMULATION
+    double z = (double)powf((float)x, -1.0f / (float)k);
+#else
+    double z = (double)exp2f(-__log2f((float)x) * (float)rk);
+#endif
+    z = fma(z * rk, fma(-x, sb_ipow(z, k), 1.0), z);
+    z = fma(z * rk, fma(-x, sb_ipow(z, k), 1.0), z);
+    return x * sb_ipow(z, k - 1);
+#endif
 }
 
 template <int N>
@@ -279,15 +311,16 @@ struct Bdf {
         sys.set_time(tn + hg);
         sys.rhs(y, f); st.nfe++;
         if (!all_finite<N>(f)) return 1;
+        const double rhg = sb_div(1.0, hg);
 #pragma unroll
-        for (int i = 0; i < N; ++i) f[i] = (f[i] - zn[1][i]) / hg;
+        for (int i = 0; i < N; ++i) f[i] = (f[i] - zn[1][i]) * rhg;
         double nrm = wrms<N>(f, ewt);
         if (QUAD) {
             double fq[NQ_];
             sys.quad(y, fq);
             if (!all_finite<NQ_>(fq)) return 1;
 #pragma unroll
-            for (int i = 0; i < NQ_; ++i) fq[i] = (fq[i] - znQ[1][i]) / hg;
+            for (int i = 0; i < NQ_; ++i) fq[i] = (fq[i] - znQ[1][i]) * rhg;
             nrm = fmax(nrm, wrms<NQ_>(fq, ewtQ));
         }
         *yddnrm = nrm;
@@ -307,19 +340,19 @@ struct Bdf {
         double hub_inv = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double d = fma(HUB_FACTOR, fabs(zn[0][i]), 1.0 / ewt[i]);
-            hub_inv = fmax(hub_inv, fabs(zn[1][i]) / d);
+            const double d = fma(HUB_FACTOR, fabs(zn[0][i]), sb_div(1.0, ewt[i]));
+            hub_inv = fmax(hub_inv, sb_div(fabs(zn[1][i]), d));
         }
         if (QUAD) {
 #pragma unroll
             for (int i = 0; i < NQ_; ++i) {
-                const double d = fma(HUB_FACTOR, fabs(znQ[0][i]), 1.0 / ewtQ[i]);
-                hub_inv = fmax(hub_inv, fabs(znQ[1][i]) / d);
+                const double d = fma(HUB_FACTOR, fabs(znQ[0][i]), sb_div(1.0, ewtQ[i]));
+                hub_inv = fmax(hub_inv, sb_div(fabs(znQ[1][i]), d));
             }
         }
         double hub = HUB_FACTOR * tdist;
-        if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
-        double hg = sqrt(hlb * hub);
+        if (hub * hub_inv > 1.0) hub = sb_div(1.0, hub_inv);
+        double hg = sb_sqrt(hlb * hub);
         if (hub < hlb) { h = sign * hg; return SB_SUCCESS; }
 
         double hs = hg, hnew = hg, yddnrm = 0.0;
@@ -336,9 +369,9 @@ struct Bdf {
                 break;
             }
             hs = hg;
-            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+            hnew = (yddnrm * hub * hub > 2.0) ? sb_sqrt(sb_div(2.0, yddnrm)) : sb_sqrt(hg * hub);
             if (count1 == HIN_ITERS) break;
-            const double hrat = hnew / hg;
+            const double hrat = sb_div(hnew, hg);
             if (hrat > 0.5 && hrat < 2.0) break;
             if (count1 > 1 && hrat > 2.0) { hnew = hg; break; }
             hg = hnew;

@@ -82,6 +82,17 @@ class Workload:
     seed: int
     adjoint: bool
     history_capacity: int
+    cotangent: str = 'ones'
+
+    def grads(self, n_states: int) -> np.ndarray:
+        """Cotangent ``g[n_t, n_s]`` shared by all instances: all ones as in the reference's
+        smoke test (sunode/test_solve.py:99), or seeded N(0, 1) for the conservative systems
+        (Robertson, SEIR), where ``sum_i y_i`` is constant so the all-ones cotangent has an
+        identically zero gradient and a trivial backward problem."""
+        if self.cotangent == 'ones':
+            return np.ones((len(self.tvals), n_states))
+        rng = np.random.default_rng(self.seed + 1000)
+        return rng.standard_normal((len(self.tvals), n_states))
 
     def draws(self, batch: int = None, offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
         """``(y0[B, n_s], params[B, n_all])``: theta = theta_med * exp(sigma * N(0, 1)), i.i.d.
@@ -105,10 +116,10 @@ def workloads() -> Dict[str, Workload]:
                            lv_t, 65536, 20261017 + 2, True, 512),
         'robertson_adj': Workload('robertson_adj', robertson, (0.04, 3e7, 1e4), 0.1,
                                   (1.0, 0.0, 0.0), 0.0, np.logspace(-4, 4, 50), 16384,
-                                  20261017 + 4, True, 4096),
+                                  20261017 + 4, True, 4096, 'normal'),
         'seir_adj': Workload('seir_adj', seir, (0.5, 0.3, 0.05, 0.2, 0.1, 0.01), 0.2,
                              (0.99, 0.0, 0.01, 0.0, 0.995, 0.0, 0.005, 0.0), 0.0,
-                             np.linspace(2, 100, 50), 262144, 20261017 + 5, True, 512),
+                             np.linspace(2, 100, 50), 262144, 20261017 + 5, True, 512, 'normal'),
     }
 
 
