@@ -267,6 +267,8 @@ def main():
         step(stats=(i == 0))
     torch.cuda.synchronize()
     n_fail = int((st_d != 0).sum().item())
+    codes, counts = torch.unique(st_d[st_d != 0], return_counts=True)
+    fail_codes = {int(c): int(n) for c, n in zip(codes.tolist(), counts.tolist())}
     mean_fwd_steps = float(sf_d[:, 0].double().mean().item())
     mean_bwd_steps = float(sb_d[:, 0].double().mean().item()) if w.adjoint else 0.0
 
@@ -385,7 +387,7 @@ def main():
         'data': 'synthetic',
         'config': config_dict(w, problem, B, world, extra={
             'l2': 'L2 flushed between timed iterations (512 MiB memset, untimed)',
-            'failed_instances': n_fail,
+            'failed_instances': n_fail, 'failed_status_rank0': fail_codes,
             'collective': 'all_gather(y_out) + all_gather(grad|lamda0) per step' if gather else 'none'}),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
     }

@@ -51,6 +51,22 @@ constexpr double NLSCOEF = 0.1, HLB_FACTOR = 100.0, HUB_FACTOR = 0.1, H_BIAS = 0
 constexpr int MXNEF1 = 3, SMALL_NEF = 2, SMALL_NST = 10, LONG_WAIT = 10, MXNCF = 10, MXNEF = 7;
 constexpr int NLS_MAXCOR = 3, MSBP = 20, MSBJ = 50, HIN_ITERS = 4;
 
+// Warp-level convergence points.  ptxas does not re-converge lanes after data-dependent loops, and
+// a lane that falls behind (Jacobian refresh, extra Newton iteration, failed error test) would
+// otherwise run the rest of the pass on its own.  `mask` is the set of lanes that entered the
+// current pass together (a ballot taken by the kernel's step loop); every one of them executes
+// every sb_sync / sb_any below exactly once per pass -- the integrator's pass is single-exit for
+// that reason.
+#ifndef SB_HOST_EMULATION
+__device__ __forceinline__ void sb_sync(unsigned mask) { __syncwarp(mask); }
+__device__ __forceinline__ bool sb_any(unsigned mask, bool pred) { return __any_sync(mask, pred) != 0; }
+__device__ __forceinline__ unsigned sb_ballot(bool pred) { return __ballot_sync(0xffffffffu, pred); }
+#else
+inline void sb_sync(unsigned) {}
+inline bool sb_any(unsigned, bool pred) { return pred; }
+inline unsigned sb_ballot(bool pred) { return pred ? 1u : 0u; }
+#endif
+
 enum NFlag { FIRST_CALL = 0, PREV_CONV_FAIL = 1, PREV_ERR_FAIL = 2 };
 enum ConvFail { NO_FAILURES = 0, FAIL_BAD_J = 1, FAIL_OTHER = 2 };
 
@@ -98,7 +114,9 @@ __device__ __forceinline__ double sb_sqrt(double x) {
     r = fma(r, fma(-hx * r, r, 0.5), r);                        // 1/sqrt(x) to ~1 ulp
     const double s = x * r;
     const double y = fma(fma(-s, s, x), 0.5 * r, s);
-    return (x > 0.0) ? y : x;                                   // 0 -> 0, nan -> nan (norms are >= 0)
+    // the SFU seed flushes denormals: below 1e-290 return 0 (absolute error < 1e-145, irrelevant
+    // for the weighted norms this is used on); NaN propagates
+    return (x >= 1e-290) ? y : ((x == x) ? 0.0 : x);
 }
 #endif
 
@@ -685,38 +703,50 @@ struct Bdf {
     }
 
     // ------------------------------------------------------------------ nonlinear solve
-    // returns 0 converged, >0 recoverable failure (conv fail / rhs recoverable)
-    __device__ __forceinline__ int nls(Sys& sys, int nflag) {
-        int convfail = (nflag == FIRST_CALL || nflag == PREV_ERR_FAIL) ? NO_FAILURES : FAIL_OTHER;
-        bool callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) ||
+    // cvNls + SUNNonlinSol_Newton + cvNlsConvTest.  `go` = this lane takes part (lanes whose pass
+    // already failed still walk through for the convergence points).  Returns 0 converged, 1
+    // recoverable failure.  The control flow is the reference's -- up to three passes (stale
+    // Jacobian -> fresh factorisation -> fresh Jacobian), up to NLS_MAXCOR Newton iterations per
+    // pass -- but every loop is closed by a warp vote so that lanes re-join after each iteration.
+    __device__ __forceinline__ int nls(Sys& sys, int nflag_, unsigned mask, bool go) {
+        int convfail = (nflag_ == FIRST_CALL || nflag_ == PREV_ERR_FAIL) ? NO_FAILURES : FAIL_OTHER;
+        bool callSetup = (nflag_ == PREV_CONV_FAIL) || (nflag_ == PREV_ERR_FAIL) || (nst == 0) ||
                          (nst >= nstlp + MSBP) || (fabs(gamrat - 1.0) > DGMAX);
         double delta[N], f[N];
-        int retval = 0;
-        sys.set_time(tn);
-        for (int attempt = 0; attempt < 3; ++attempt) {
+        int retval = 1;
+        bool done = !go;
+        if (go) sys.set_time(tn);
+        for (int pass = 0; pass < 3; ++pass) {
+            bool live = !done;
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) { acor[i] = 0.0; ycur[i] = zn[0][i]; }
-            sys.rhs(ycur, f); st.nfe++;
-            // a failure before the Newton loop (residual or setup) is returned without a retry
-            if (!all_finite<N>(f)) return 1;
-            if (callSetup) {
-                retval = lsetup(sys, convfail, ycur);
+                for (int i = 0; i < N; ++i) { acor[i] = 0.0; ycur[i] = zn[0][i]; }
+                sys.rhs(ycur, f); st.nfe++;
+                // a failure before the Newton loop (residual or setup) is returned without a retry
+                if (!all_finite<N>(f)) { done = true; live = false; }
+            }
+            if (live && callSetup) {
+                const int r = lsetup(sys, convfail, ycur);
                 st.nsetups++;
                 callSetup = false;
                 gamrat = 1.0; gammap = gamma; crate = 1.0; nstlp = nst;
-                if (retval != 0) return 1;
+                if (r != 0) { done = true; live = false; }
             }
-            {
+            sb_sync(mask);
+            bool run = live;
+            if (run) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) delta[i] = fma(gamma, f[i], -fma(rl1, zn[1][i], acor[i]));
                 // delta now holds -(rl1*zn1 + acor - gamma*f) = -G
-                for (int m = 0;; ++m) {
+            }
+            for (int m = 0; m < NLS_MAXCOR; ++m) {
+                if (run) {
                     st.nni++;
                     lu_solve<N>(M, piv, delta);
                     if (gamrat != 1.0) {
-                        const double s = sb_div(2.0, 1.0 + gamrat);
+                        const double sc = sb_div(2.0, 1.0 + gamrat);
 #pragma unroll
-                        for (int i = 0; i < N; ++i) delta[i] *= s;
+                        for (int i = 0; i < N; ++i) delta[i] *= sc;
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) { acor[i] += delta[i]; ycur[i] = zn[0][i] + acor[i]; }
@@ -726,25 +756,33 @@ struct Bdf {
                     if (dcon <= 1.0) {
                         acnrm = (m == 0) ? del : wrms<N>(acor, ewt);
                         jcur = false;
-                        return 0;
-                    }
-                    if (!(dcon > 1.0)) { retval = 1; break; }              // NaN
-                    if (m >= 1 && del > RDIV * delp) { retval = 1; break; }
-                    delp = del;
-                    if (m + 1 >= NLS_MAXCOR) { retval = 1; break; }
-                    sys.rhs(ycur, f); st.nfe++;
-                    if (!all_finite<N>(f)) { retval = 1; break; }
+                        retval = 0; done = true; run = false;
+                    } else if (!(dcon > 1.0)) {                       // NaN
+                        run = false;
+                    } else if (m >= 1 && del > RDIV * delp) {         // diverging
+                        run = false;
+                    } else {
+                        delp = del;
+                        if (m + 1 >= NLS_MAXCOR) {
+                            run = false;
+                        } else {
+                            sys.rhs(ycur, f); st.nfe++;
+                            if (!all_finite<N>(f)) run = false;
 #pragma unroll
-                    for (int i = 0; i < N; ++i) delta[i] = fma(gamma, f[i], -fma(rl1, zn[1][i], acor[i]));
+                            for (int i = 0; i < N; ++i)
+                                delta[i] = fma(gamma, f[i], -fma(rl1, zn[1][i], acor[i]));
+                        }
+                    }
                 }
+                if (!sb_any(mask, run)) break;
             }
             // recoverable failure with a stale Jacobian: one more try with a fresh one
-            if (retval > 0 && !jcur) {
-                callSetup = true;
-                convfail = FAIL_BAD_J;
-                continue;
+            bool retry = false;
+            if (live && !done) {
+                if (!jcur) { callSetup = true; convfail = FAIL_BAD_J; retry = true; }
+                else done = true;
             }
-            break;
+            if (!sb_any(mask, retry)) break;
         }
         return retval;
     }
@@ -874,10 +912,11 @@ struct Bdf {
     }
 
     // ------------------------------------------------------------------ one internal step (cvStep)
-    // One pass of cvStep's predict / solve / test loop.  Returns SB_SUCCESS when the step is
-    // complete, SB_TRY_AGAIN when the pass failed recoverably (the history has been restored and
-    // rescaled; call again), < 0 on a fatal failure.
-    __device__ __forceinline__ int attempt(Sys& sys) {
+    // One pass of cvStep's predict / solve / test loop, entered together by the lanes in `mask`.
+    // Returns SB_SUCCESS when the step is complete, SB_TRY_AGAIN when the pass failed recoverably
+    // (the retry is queued in `pend`; call again), < 0 on a fatal failure.  Single exit: a lane
+    // whose pass has failed keeps walking (doing nothing) through the remaining convergence points.
+    __device__ __forceinline__ int attempt(Sys& sys, unsigned mask) {
         if (!in_step) {
             step_t0 = tn;
             ncf = 0; nef = 0; nefQ = 0; nflag = FIRST_CALL;
@@ -885,68 +924,88 @@ struct Bdf {
             if (nst > 0 && hprime != h) pend = PEND_RESCALE | ((qprime != q) ? PEND_ORDER : 0);
             in_step = true;
         }
+        int result = SB_SUCCESS;
         if (pend != 0) {
             const int pr = apply_pending(sys);
-            if (pr != SB_SUCCESS) { in_step = false; return pr; }
+            if (pr != SB_SUCCESS) { in_step = false; result = pr; }
         }
-        predict();
-        set_coeffs();
-        const int nr = nls(sys, nflag);
-        if (nr != 0) {
-            st.ncfn++; ncf++;
-            etamax = 1.0;
-            if (ncf == MXNCF) { in_step = false; return SB_CONV_FAILURE; }
-            eta = ETACF;
-            nflag = PREV_CONV_FAIL;
-            pend = PEND_RESTORE | PEND_RESCALE;
-            return SB_TRY_AGAIN;
+        bool go = (result == SB_SUCCESS);
+        sb_sync(mask);
+        if (go) {
+            predict();
+            set_coeffs();
         }
-        double dsm = acnrm * tq[2];
-        if (!(dsm <= 1.0)) {
-            nef++;
-            nflag = PREV_ERR_FAIL;
-            const int r = error_test_failed(dsm, nef);
-            if (r < 0) { in_step = false; return r; }
-            return SB_TRY_AGAIN;
-        }
-        if (QUAD) {
-            ncf = 0; nef = 0;
-            double fq[NQ_];
-            sys.quad(ycur, fq);
-            if (!all_finite<NQ_>(fq)) {
+        const int nr = nls(sys, nflag, mask, go);
+        double dsm = 0.0;
+        if (go) {
+            if (nr != 0) {
+                // cvHandleNFlag
                 st.ncfn++; ncf++;
                 etamax = 1.0;
-                if (ncf == MXNCF) { in_step = false; return SB_REPTD_RHSFUNC_ERR; }
-                eta = ETACF;
-                nflag = PREV_CONV_FAIL;
-                pend = PEND_RESTORE | PEND_RESCALE;
-                return SB_TRY_AGAIN;
+                go = false;
+                if (ncf == MXNCF) { in_step = false; result = SB_CONV_FAILURE; }
+                else {
+                    eta = ETACF;
+                    nflag = PREV_CONV_FAIL;
+                    pend = PEND_RESTORE | PEND_RESCALE;
+                    result = SB_TRY_AGAIN;
+                }
+            } else {
+                dsm = acnrm * tq[2];
+                if (!(dsm <= 1.0)) {
+                    nef++;
+                    nflag = PREV_ERR_FAIL;
+                    const int r = error_test_failed(dsm, nef);
+                    go = false;
+                    if (r < 0) { in_step = false; result = r; }
+                    else result = SB_TRY_AGAIN;
+                }
             }
-#pragma unroll
-            for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
-            const double dsmQ = wrms<NQ_>(acorQ, ewtQ) * tq[2];
-            if (!(dsmQ <= 1.0)) {
-                nefQ++;
-                nflag = PREV_ERR_FAIL;
-                const int r = error_test_failed(dsmQ, nefQ);
-                if (r < 0) { in_step = false; return r; }
-                return SB_TRY_AGAIN;
-            }
-            dsm = fmax(dsm, dsmQ);
         }
-        complete_step();
-        prepare_next_step(dsm);
-        etamax = (nst <= SMALL_NST) ? ETAMX2 : ETAMX3;
-        // (CVODES rescales acor by tq[2] here to expose the local error estimate; nothing on this
-        // path reads it before the next step overwrites it, so it is not materialised.)
-        in_step = false;
-        return SB_SUCCESS;
-    }
-
-    __device__ __forceinline__ int step(Sys& sys) {
-        int r;
-        do { r = attempt(sys); } while (r == SB_TRY_AGAIN);
-        return r;
+        if (QUAD) {
+            sb_sync(mask);
+            if (go) {
+                ncf = 0; nef = 0;
+                double fq[NQ_];
+                sys.quad(ycur, fq);
+                if (!all_finite<NQ_>(fq)) {
+                    st.ncfn++; ncf++;
+                    etamax = 1.0;
+                    go = false;
+                    if (ncf == MXNCF) { in_step = false; result = SB_REPTD_RHSFUNC_ERR; }
+                    else {
+                        eta = ETACF;
+                        nflag = PREV_CONV_FAIL;
+                        pend = PEND_RESTORE | PEND_RESCALE;
+                        result = SB_TRY_AGAIN;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
+                    const double dsmQ = wrms<NQ_>(acorQ, ewtQ) * tq[2];
+                    if (!(dsmQ <= 1.0)) {
+                        nefQ++;
+                        nflag = PREV_ERR_FAIL;
+                        const int r = error_test_failed(dsmQ, nefQ);
+                        go = false;
+                        if (r < 0) { in_step = false; result = r; }
+                        else result = SB_TRY_AGAIN;
+                    } else {
+                        dsm = fmax(dsm, dsmQ);
+                    }
+                }
+            }
+        }
+        sb_sync(mask);
+        if (go) {
+            complete_step();
+            prepare_next_step(dsm);
+            etamax = (nst <= SMALL_NST) ? ETAMX2 : ETAMX3;
+            // (CVODES rescales acor by tq[2] here to expose the local error estimate; nothing on
+            // this path reads it before the next step overwrites it, so it is not materialised.)
+            in_step = false;
+        }
+        return result;
     }
 
     // ------------------------------------------------------------------ dense output

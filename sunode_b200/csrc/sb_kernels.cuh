@@ -35,15 +35,6 @@ constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-// warp vote / convergence point (all 32 lanes of every warp take part, see forward_instance)
-#ifndef SB_HOST_EMULATION
-__device__ __forceinline__ bool sb_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
-__device__ __forceinline__ void sb_converge() { __syncwarp(0xffffffffu); }
-#else
-inline bool sb_any(bool pred) { return pred; }
-inline void sb_converge() {}
-#endif
-
 // ------------------------------------------------------------------------------------ forward
 struct FwdSys {
     double p[NP_];
@@ -117,22 +108,23 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
                 if (++k == a.n_t) { work = false; break; }
             }
         }
-        if (!sb_any(work)) break;
-        if (work) {
-            const double tout = a.tvals[k];
-            if (bdf.nst == 0 && !bdf.in_step) {
-                status = bdf.first_call(sys, tout);
+        if (work && !bdf.in_step) {
+            // what CVode() does before it calls cvStep
+            if (bdf.nst == 0) {
+                status = bdf.first_call(sys, a.tvals[k]);
                 if (status == SB_SUCCESS && hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0]);
             }
-            if (status == SB_SUCCESS && !bdf.in_step) {
+            if (status == SB_SUCCESS) {
                 if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
                 else if (hist && bdf.nst + 1 >= a.hist_cap) status = SB_TOO_MUCH_WORK;
                 else status = bdf.pre_step_checks();
             }
+            work = status == SB_SUCCESS;
         }
-        sb_converge();
-        if (work && status == SB_SUCCESS) {
-            const int r = bdf.attempt(sys);
+        const unsigned mask = sb_ballot(work);
+        if (mask == 0u) break;
+        if (work) {
+            const int r = bdf.attempt(sys, mask);
             if (r == SB_SUCCESS) {
                 nloc++;
                 if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
@@ -301,9 +293,10 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
                     else status = bdf.pre_step_checks();
                     work = status == SB_SUCCESS;
                 }
-                if (!sb_any(work)) break;
+                const unsigned mask = sb_ballot(work);
+                if (mask == 0u) break;
                 if (work) {
-                    const int r = bdf.attempt(sys);
+                    const int r = bdf.attempt(sys, mask);
                     if (r == SB_SUCCESS) {
                         nloc++;
                         bdf.snap_to_tstop();
