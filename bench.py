@@ -114,13 +114,22 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1 per rank, which
+    must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
     """The oracle (CPU restatement of the reference path) on the host cores, bounded sample."""
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8)
     y0, theta = w.draws(n_sample)
     grads = w.grads(problem.n_states)
-    cores = threads or max_threads()
+    cores = threads or host_threads()
     best = None
     for _ in range(repeats):
         t = time.perf_counter()
@@ -141,7 +150,7 @@ def run_reference(args, w, problem, rank, world):
     orc = Oracle(problem, rtol=1e-8, atol=1e-8)
     y0, theta = w.draws(n_sample)
     grads = w.grads(problem.n_states)
-    cores = max_threads()
+    cores = host_threads()
 
     def step():
         if w.adjoint:

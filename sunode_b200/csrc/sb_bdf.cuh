@@ -89,16 +89,30 @@ __device__ __forceinline__ void static_for(F&& f) {
 // well-scaled normal numbers, so it uses branch-free Newton sequences seeded by the SFU
 // approximations instead: results are within an ulp of the IEEE ones.  -DSB_EXACT_MATH restores
 // the IEEE operations (out of line, to keep the code small).
-#if defined(SB_HOST_EMULATION)
-__device__ __forceinline__ double sb_div(double a, double b) { return a / b; }
-__device__ __forceinline__ double sb_sqrt(double a) { return sqrt(a); }
-#elif defined(SB_EXACT_MATH)
+#if defined(SB_EXACT_MATH) && !defined(SB_HOST_EMULATION)
 __device__ __noinline__ double sb_div(double a, double b) { return a / b; }
 __device__ __noinline__ double sb_sqrt(double a) { return sqrt(a); }
+#elif defined(SB_EXACT_MATH)
+__device__ __forceinline__ double sb_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double sb_sqrt(double a) { return sqrt(a); }
 #else
+#ifdef SB_HOST_EMULATION
+// host stand-ins for the SFU seeds: the exact value with the low 32 mantissa bits cleared
+static inline double sb_seed_trunc(double v) {
+    unsigned long long u; std::memcpy(&u, &v, 8); u &= 0xffffffff00000000ULL; std::memcpy(&v, &u, 8); return v;
+}
+static inline double sb_rcp_seed(double b) { return sb_seed_trunc(1.0 / b); }
+static inline double sb_rsqrt_seed(double x) { return sb_seed_trunc(1.0 / std::sqrt(x)); }
+#else
+__device__ __forceinline__ double sb_rcp_seed(double b) {
+    double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b)); return r;       // MUFU.RCP64H
+}
+__device__ __forceinline__ double sb_rsqrt_seed(double x) {
+    double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;     // MUFU.RSQ64H
+}
+#endif
 __device__ __forceinline__ double sb_div(double a, double b) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));      // MUFU.RCP64H: ~20 good bits
+    double r = sb_rcp_seed(b);                                  // ~20 good bits
     double e = fma(-b, r, 1.0);
     r = fma(r, e, r);
     e = fma(-b, r, 1.0);
@@ -107,8 +121,7 @@ __device__ __forceinline__ double sb_div(double a, double b) {
     return fma(fma(-b, q, a), r, q);                            // residual correction
 }
 __device__ __forceinline__ double sb_sqrt(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));    // MUFU.RSQ64H
+    double r = sb_rsqrt_seed(x);
     const double hx = 0.5 * x;
     r = fma(r, fma(-hx * r, r, 0.5), r);
     r = fma(r, fma(-hx * r, r, 0.5), r);                        // 1/sqrt(x) to ~1 ulp
