@@ -1,7 +1,12 @@
-"""sunode_b200: batched stiff-ODE + adjoint engine for B200 behind sunode's API."""
-from .symode import SympyProblem
+"""sunode_b200: batched stiff-ODE + adjoint engine for B200 behind sunode's API.
+
+Import surface of the reference kept (``sunode/__init__.py``): ``SympyProblem``, ``solver``
+(``Solver``, ``AdjointSolver``, ``SolverError``), ``wrappers.as_pytensor``, ``_cvodes.lib``.
+"""
+from . import _cvodes, basic, dtypesubset, problem, symode
 from .basic import SolverError
+from .symode import SympyProblem
 
 __version__ = "0.1.0"
 
-__all__ = ["SympyProblem", "SolverError"]
+__all__ = ["SympyProblem", "SolverError", "symode", "basic", "dtypesubset", "problem", "_cvodes"]

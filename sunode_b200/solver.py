@@ -81,6 +81,17 @@ class _ParamsMixin:
     def set_remaining_params(self, params):
         self._problem.update_remaining_params(self._user_data, params)
 
+    # tokens for the README-style raw pokes (sunode_b200._cvodes.lib)
+    @property
+    def _ode(self):
+        from ._cvodes import OdeToken
+        return OdeToken(self, False)
+
+    @property
+    def _odeB(self):
+        from ._cvodes import OdeToken
+        return OdeToken(self, True)
+
     # ---- helpers for the batch entry points
     def _flat_params(self) -> np.ndarray:
         return self._problem.flat_params(self._user_data)
