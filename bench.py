@@ -145,7 +145,7 @@ def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
 def run_reference(args, w, problem, rank, world):
     if rank != 0:
         return
-    n_sample = args.cpu_sample or 4096
+    n_sample = args.cpu_sample or {'lv_adj': 16384, 'lv_fwd': 65536}.get(w.name, 1024)
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8)
     y0, theta = w.draws(n_sample)
@@ -401,7 +401,8 @@ def main():
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
     }
     if not args.no_cpu_baseline:
-        n_sample = args.cpu_sample or min(B, 8192)
+        # ~20-40 s of CPU work for the LV workload (spread over the host threads)
+        n_sample = args.cpu_sample or min(B, {'lv_adj': 32768, 'lv_fwd': 65536}.get(w.name, 2048))
         v, cores, secs = cpu_baseline(w, problem, n_sample, w.adjoint)
         line['cpu_baseline'] = {
             'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',

@@ -247,8 +247,39 @@ __device__ __forceinline__ void lu_solve(const double* a, const int* piv, double
     }
 }
 
-struct Stats {
-    int nst, nfe, nje, nsetups, netf, ncfn, nni;
+// ---- per-lane slab in shared memory ---------------------------------------------------------------
+// Resident warps per SM are what hides the FP64 latency of this kernel (measured: throughput grows
+// almost linearly from 2 to 8 warps/SM), and the register file alone holds 8 warps of the
+// integrator.  State that is touched a few times per step -- step-size history, method
+// coefficients, the saved correction, the saved Jacobian, counters -- therefore lives in a
+// per-lane column of shared memory (slot s of lane l at word s * SB_LANES + l: conflict-free), which
+// leaves the registers to the Nordsieck array and the Newton iteration.
+#ifndef SB_HOST_EMULATION
+extern __shared__ double sb_slab_mem[];
+#define SB_LANES SB_BLOCK
+__device__ __forceinline__ double* sb_slab() { return sb_slab_mem + threadIdx.x; }
+#else
+#define SB_LANES 1
+static thread_local double sb_slab_host[2048];
+inline double* sb_slab() { return sb_slab_host; }
+#endif
+template <int OFF> struct SlabArr {          // double array
+    __device__ __forceinline__ double& operator[](int i) const { return sb_slab()[(OFF + i) * SB_LANES]; }
+};
+template <int OFF> struct SlabVal {          // double scalar
+    __device__ __forceinline__ operator double() const { return sb_slab()[OFF * SB_LANES]; }
+    __device__ __forceinline__ double operator=(double v) const { sb_slab()[OFF * SB_LANES] = v; return v; }
+};
+template <int OFF> struct SlabInt {          // int scalar (one slot each)
+    __device__ __forceinline__ int& ref() const { return *reinterpret_cast<int*>(&sb_slab()[OFF * SB_LANES]); }
+    __device__ __forceinline__ operator int() const { return ref(); }
+    __device__ __forceinline__ int operator=(int v) const { ref() = v; return v; }
+    __device__ __forceinline__ int operator++(int) const { return ref()++; }
+};
+
+template <int O> struct Stats {
+    SlabInt<O + 0> nst; SlabInt<O + 1> nfe; SlabInt<O + 2> nje; SlabInt<O + 3> nsetups;
+    SlabInt<O + 4> netf; SlabInt<O + 5> ncfn; SlabInt<O + 6> nni;
 };
 
 template <int N, int NQ, class Sys>
@@ -256,28 +287,41 @@ struct Bdf {
     static constexpr int NQ_ = NQ > 0 ? NQ : 1;
     static constexpr bool QUAD = NQ > 0;
 
-    // Nordsieck arrays
-    double zn[SB_LMAX][N], zsave[N], acor[N], ewt[N];
-    double znQ[SB_LMAX][NQ_], zsaveQ[NQ_], acorQ[NQ_], ewtQ[NQ_];
+    // slab layout (slots of 8 bytes per lane)
+    static constexpr int O_ZSAVE = 0, O_ZSAVEQ = O_ZSAVE + N, O_TAU = O_ZSAVEQ + NQ_,
+                         O_L = O_TAU + SB_LMAX + 1, O_TQ = O_L + SB_LMAX, O_SAVEDJ = O_TQ + 6,
+                         O_SCAL = O_SAVEDJ + N * N, O_INT = O_SCAL + 4, SLAB_SLOTS = O_INT + 10;
+
+    // Nordsieck arrays (registers)
+    double zn[SB_LMAX][N], acor[N], ewt[N];
+    double znQ[SB_LMAX][NQ_], acorQ[NQ_], ewtQ[NQ_];
     double ycur[N];                 // zn[0] + acor after the nonlinear solve
+    SlabArr<O_ZSAVE> zsave;         // the correction CVODES parks in zn[qmax]
+    SlabArr<O_ZSAVEQ> zsaveQ;
     // step / order control
-    double tau[SB_LMAX + 1], l[SB_LMAX], tq[6];
-    double h, hprime, hscale, eta, etamax, tn, hu;
-    double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
-    double tstop;
-    int q, qprime, qwait, L, qu;
-    bool tstopset, jcur;
-    // tolerances
-    double reltol, abstol[N], reltolQ, abstolQ;
+    SlabArr<O_TAU> tau;             // [SB_LMAX + 1]
+    SlabArr<O_L> l;                 // [SB_LMAX]
+    SlabArr<O_TQ> tq;               // [6]
+    double h, hprime, hscale, eta, etamax, tn;
+    double rl1, gamma, gamrat, crate, delp, acnrm;
+    SlabVal<O_SCAL + 0> step_t0;
+    SlabVal<O_SCAL + 1> saved_tq5;
+    SlabVal<O_SCAL + 2> hu;
+    SlabVal<O_SCAL + 3> gammap;
+    int q, qprime, qwait, L;
+    bool jcur;
     // linear solver
-    double savedJ[N * N], M[N * N];
+    SlabArr<O_SAVEDJ> savedJ;       // [N * N], column-major
+    double M[N * N];
     int piv[N];
     // counters
-    int nst, nstlp, nstlj;
-    Stats st;
+    int nst;
+    SlabInt<O_INT + 7> nstlp;
+    SlabInt<O_INT + 8> nstlj;
+    SlabInt<O_INT + 9> qu;
+    Stats<O_INT> st;
     // a step in flight (cvStep's locals): one call of attempt() is one pass of cvStep's retry loop,
     // so that the lanes of a warp can be re-converged between passes by the caller
-    double step_t0;
     int ncf, nef, nefQ, nflag;
     bool in_step;
     // History manipulations requested by the previous pass (failed pass: restore + rescale, maybe
@@ -306,27 +350,28 @@ struct Bdf {
         q = 1; L = 2; qwait = 2; qprime = 1; etamax = ETAMX1; qu = 0; hu = 0.0;
         nst = 0; nstlp = 0; nstlj = 0;
         saved_tq5 = 0.0; jcur = false; crate = 1.0; delp = 0.0; acnrm = 0.0;
-        tstopset = false; tstop = 0.0;
-        h = hprime = hscale = 0.0; eta = 1.0; gamma = gammap = gamrat = 1.0; rl1 = 1.0;
+        h = hprime = hscale = 0.0; eta = 1.0; gamma = gamrat = 1.0; gammap = 1.0; rl1 = 1.0;
         in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL; pend = 0;
     }
 
     __device__ __forceinline__ void clear_stats() {
-        st.nst = st.nfe = st.nje = st.nsetups = st.netf = st.ncfn = st.nni = 0;
+        st.nst = 0; st.nfe = 0; st.nje = 0; st.nsetups = 0; st.netf = 0; st.ncfn = 0; st.nni = 0;
     }
 
-    __device__ __forceinline__ bool set_ewt() {
+    // tolerances are launch constants: they are read through `sys` (kernel arguments / constant
+    // bank) where they are needed instead of occupying registers
+    __device__ __forceinline__ bool set_ewt(const Sys& sys) {
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double d = fma(reltol, fabs(zn[0][i]), abstol[i]);
+            const double d = fma(sys.rtol(), fabs(zn[0][i]), sys.atol(i));
             ok = ok && (d > 0.0);
             ewt[i] = sb_div(1.0, d);
         }
         if (QUAD) {
 #pragma unroll
             for (int i = 0; i < NQ_; ++i) {
-                const double d = fma(reltolQ, fabs(znQ[0][i]), abstolQ);
+                const double d = fma(sys.rtolQ(), fabs(znQ[0][i]), sys.atolQ());
                 ok = ok && (d > 0.0);
                 ewtQ[i] = sb_div(1.0, d);
             }
@@ -415,7 +460,7 @@ struct Bdf {
 
     // The part of CVode() that runs when nst == 0: f(t0, y0), initial h, scale zn[1].
     __device__ __forceinline__ int first_call(Sys& sys, double tout) {
-        if (!set_ewt()) return SB_ILL_INPUT;
+        if (!set_ewt(sys)) return SB_ILL_INPUT;
         sys.set_time(tn);
         sys.rhs(zn[0], zn[1]); st.nfe++;
         if (!all_finite<N>(zn[1])) return SB_FIRST_RHSFUNC_ERR;
@@ -423,12 +468,12 @@ struct Bdf {
             sys.quad(zn[0], znQ[1]);
             if (!all_finite<NQ_>(znQ[1])) return SB_RHSFUNC_FAIL;
         }
-        if (tstopset && (tstop - tn) * (tout - tn) <= 0.0) return SB_ILL_INPUT;
+        if (Sys::TSTOP && (sys.tstop() - tn) * (tout - tn) <= 0.0) return SB_ILL_INPUT;
         double tout_hin = tout;
-        if (tstopset && (tout - tn) * (tout - tstop) > 0.0) tout_hin = tstop;
+        if (Sys::TSTOP && (tout - tn) * (tout - sys.tstop()) > 0.0) tout_hin = sys.tstop();
         const int hflag = hin(sys, tout_hin);
         if (hflag != SB_SUCCESS) return hflag;
-        if (tstopset && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * SB_UROUND);
+        if (Sys::TSTOP && (tn + h - sys.tstop()) * h > 0.0) h = (sys.tstop() - tn) * (1.0 - 4.0 * SB_UROUND);
         hscale = h; hprime = h;
 #pragma unroll
         for (int i = 0; i < N; ++i) zn[1][i] *= h;
@@ -457,9 +502,9 @@ struct Bdf {
         hscale = h;
     }
 
-    __device__ __forceinline__ void predict() {
+    __device__ __forceinline__ void predict(const Sys& sys) {
         tn += h;
-        if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+        if (Sys::TSTOP && (tn - sys.tstop()) * h > 0.0) tn = sys.tstop();
 #pragma unroll
         for (int k = 1; k < SB_LMAX; ++k)
 #pragma unroll
@@ -634,9 +679,10 @@ struct Bdf {
     // ------------------------------------------------------------------ cvSetBDF + cvSetTqBDF
     __device__ __forceinline__ void set_coeffs() {
         double xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0, hsum = h;
+        double lc[SB_LMAX];          // the polynomial is built in registers, then parked in the slab
 #pragma unroll
-        for (int i = 0; i < SB_LMAX; ++i) l[i] = 0.0;
-        l[0] = l[1] = 1.0;
+        for (int i = 0; i < SB_LMAX; ++i) lc[i] = 0.0;
+        lc[0] = lc[1] = 1.0;
         if (q > 1) {
 #pragma unroll
             for (int j = 2; j < SB_QMAX; ++j) {
@@ -646,50 +692,47 @@ struct Bdf {
                     alpha0 -= 1.0 / (double)j;
 #pragma unroll
                     for (int i = SB_QMAX; i >= 1; --i)
-                        if (i <= j) l[i] = fma(l[i - 1], xi_inv, l[i]);
+                        if (i <= j) lc[i] = fma(lc[i - 1], xi_inv, lc[i]);
                 }
             }
-            alpha0 -= 1.0 / (double)q;
-            xistar_inv = -l[1] - alpha0;
-            double tau_qm1 = 0.0;
-            static_for<1, SB_LMAX>([&](auto J_) {
-                constexpr int j = SB_IDX(J_);
-                tau_qm1 = (j == q - 1) ? tau[j] : tau_qm1;
-            });
-            hsum += tau_qm1;
+            alpha0 -= sb_rk_table[q];
+            xistar_inv = -lc[1] - alpha0;
+            hsum += tau[q - 1];
             xi_inv = sb_div(h, hsum);
-            alpha0_hat = -l[1] - xi_inv;
+            alpha0_hat = -lc[1] - xi_inv;
 #pragma unroll
             for (int i = SB_QMAX; i >= 1; --i)
-                if (i <= q) l[i] = fma(l[i - 1], xistar_inv, l[i]);
+                if (i <= q) lc[i] = fma(lc[i - 1], xistar_inv, lc[i]);
         }
-        double lq = 1.0, tau_q = 0.0;
+        double lq = 1.0;
         static_for<1, SB_LMAX>([&](auto J_) {
             constexpr int j = SB_IDX(J_);
-            lq = (j == q) ? l[j] : lq;
-            tau_q = (j == q) ? tau[j] : tau_q;
+            lq = (j == q) ? lc[j] : lq;
         });
+#pragma unroll
+        for (int j = 0; j < SB_LMAX; ++j) l[j] = lc[j];
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        tq[2] = fabs(sb_div(A1, alpha0 * A2));
+        const double tq2 = fabs(sb_div(A1, alpha0 * A2));
+        tq[2] = tq2;
         tq[5] = fabs(sb_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
                 const double C = sb_div(xistar_inv, lq);
-                const double A3 = alpha0 + 1.0 / (double)q;
+                const double A3 = alpha0 + sb_rk_table[q];
                 const double A4 = alpha0_hat + xi_inv;
                 const double Cpinv = sb_div(1.0 - A4 + A3, A3);
                 tq[1] = fabs(C * Cpinv);
             } else tq[1] = 1.0;
-            hsum += tau_q;
+            hsum += tau[q];
             xi_inv = sb_div(h, hsum);
-            const double A5 = alpha0 - (1.0 / (double)(q + 1));
+            const double A5 = alpha0 - sb_rk_table[q + 1];
             const double A6 = alpha0_hat - xi_inv;
             const double Cppinv = sb_div(1.0 - A6 + A5, A2);
             tq[3] = fabs(sb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq[4] = sb_div(NLSCOEF, tq[2]);
-        rl1 = sb_div(1.0, l[1]);
+        tq[4] = sb_div(NLSCOEF, tq2);
+        rl1 = sb_div(1.0, lc[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
         gamrat = (nst > 0) ? sb_div(gamma, gammap) : 1.0;
@@ -698,18 +741,23 @@ struct Bdf {
     // ------------------------------------------------------------------ linear setup
     // returns 0 ok, 1 recoverable
     __device__ __forceinline__ int lsetup(Sys& sys, int convfail, const double* ypred) {
-        const double dgamma = fabs(sb_div(gamma, gammap) - 1.0);
+        // |gamma/gammap - 1|: set_coeffs computed that ratio for this pass already
+        const double dgamma = fabs(gamrat - 1.0);
         const bool jbad = (nst == 0) || (nst > nstlj + MSBJ) ||
                           (convfail == FAIL_BAD_J && dgamma < LS_DGMAX) || (convfail == FAIL_OTHER);
         if (jbad) {
             st.nje++; nstlj = nst; jcur = true;
-            sys.jac(ypred, savedJ);
-            if (!all_finite<N * N>(savedJ)) return 1;
+            sys.jac(ypred, M);
+            if (!all_finite<N * N>(M)) return 1;
+#pragma unroll
+            for (int k = 0; k < N * N; ++k) savedJ[k] = M[k];
         } else {
             jcur = false;
+#pragma unroll
+            for (int k = 0; k < N * N; ++k) M[k] = savedJ[k];
         }
 #pragma unroll
-        for (int k = 0; k < N * N; ++k) M[k] = -gamma * savedJ[k];
+        for (int k = 0; k < N * N; ++k) M[k] = -gamma * M[k];
 #pragma unroll
         for (int i = 0; i < N; ++i) M[i + N * i] += 1.0;
         return lu_factor<N>(M, piv) ? 0 : 1;
@@ -804,8 +852,7 @@ struct Bdf {
     __device__ __forceinline__ void complete_step() {
         nst++; st.nst++;
         hu = h; qu = q;
-#pragma unroll
-        for (int i = SB_QMAX; i >= 2; --i) tau[i] = (i <= q) ? tau[i - 1] : tau[i];
+        for (int i = q; i >= 2; --i) tau[i] = tau[i - 1];
         if (q == 1 && nst > 1) tau[2] = tau[1];
         tau[1] = h;
         // l[j] == 0 and zn[j] == 0 for j > q, so the update runs over all rows
@@ -945,7 +992,7 @@ struct Bdf {
         bool go = (result == SB_SUCCESS);
         sb_sync(mask);
         if (go) {
-            predict();
+            predict(sys);
             set_coeffs();
         }
         const int nr = nls(sys, nflag, mask, go);
@@ -1045,8 +1092,8 @@ struct Bdf {
     }
 
     // Per-step bookkeeping CVode() does around cvStep for nst > 0.  Returns <0 on failure.
-    __device__ __forceinline__ int pre_step_checks() {
-        if (nst > 0 && !set_ewt()) return SB_ILL_INPUT;
+    __device__ __forceinline__ int pre_step_checks(const Sys& sys) {
+        if (nst > 0 && !set_ewt(sys)) return SB_ILL_INPUT;
         double nrm = wrms<N>(zn[0], ewt);
         if (QUAD) nrm = fmax(nrm, wrms<NQ_>(znQ[0], ewtQ));
         if (SB_UROUND * nrm > 1.0) return SB_TOO_MUCH_ACC;
@@ -1055,15 +1102,15 @@ struct Bdf {
 
     // tstop handling after a successful step (CVode loop, "tstop" blocks).  Returns true when the
     // integration reached tstop.
-    __device__ __forceinline__ void snap_to_tstop() {
-        if (tstopset) {
+    __device__ __forceinline__ void snap_to_tstop(const Sys& sys) {
+        if (Sys::TSTOP) {
             const double troundoff = FUZZ * SB_UROUND * (fabs(tn) + fabs(h));
-            if (fabs(tn - tstop) <= troundoff) tn = tstop;
+            if (fabs(tn - sys.tstop()) <= troundoff) tn = sys.tstop();
         }
     }
-    __device__ __forceinline__ void limit_to_tstop() {
-        if (tstopset && (tn + hprime - tstop) * h > 0.0) {
-            hprime = (tstop - tn) * (1.0 - 4.0 * SB_UROUND);
+    __device__ __forceinline__ void limit_to_tstop(const Sys& sys) {
+        if (Sys::TSTOP && (tn + hprime - sys.tstop()) * h > 0.0) {
+            hprime = (sys.tstop() - tn) * (1.0 - 4.0 * SB_UROUND);
             eta = sb_div(hprime, h);
         }
     }

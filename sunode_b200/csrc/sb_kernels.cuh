@@ -13,15 +13,14 @@
 // communication at all.  Inputs/outputs are instance-major (a batch-1 view is byte-compatible
 // with the reference's [n_t, n_s] C-order buffers).
 #pragma once
-#include "sb_args.h"
-#include "sb_bdf.cuh"
-
 #ifndef SB_BLOCK
-#define SB_BLOCK 128
+#define SB_BLOCK 32
 #endif
 #ifndef SB_MIN_BLOCKS
 #define SB_MIN_BLOCKS 1
 #endif
+#include "sb_args.h"
+#include "sb_bdf.cuh"
 
 namespace sb {
 
@@ -37,8 +36,16 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000
 
 // ------------------------------------------------------------------------------------ forward
 struct FwdSys {
+    static constexpr bool TSTOP = false;
+    const SbForwardArgs& a;
     double p[NP_];
     double t;
+    __device__ __forceinline__ explicit FwdSys(const SbForwardArgs& a_) : a(a_) {}
+    __device__ __forceinline__ double rtol() const { return a.rtol; }
+    __device__ __forceinline__ double atol(int i) const { return __ldg(a.atol + i); }
+    __device__ __forceinline__ double rtolQ() const { return 0.0; }
+    __device__ __forceinline__ double atolQ() const { return 1.0; }
+    __device__ __forceinline__ double tstop() const { return 0.0; }
     __device__ __forceinline__ void set_time(double t_) { t = t_; }
     __device__ __forceinline__ void rhs(const double* y, double* out) const { sb_rhs(t, y, p, out); }
     __device__ __forceinline__ void jac(const double* y, double* J) const { sb_jac(t, y, p, J); }
@@ -65,17 +72,13 @@ __device__ __forceinline__ void store_point(double* hist, int idx, double t, int
 __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst, bool valid) {
     using Integrator = Bdf<NS, 0, FwdSys>;
     Integrator bdf;
-    FwdSys sys;
+    FwdSys sys(a);
     double y0[NS];
     if (!valid) inst = 0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) y0[i] = a.y0[inst * NS + i];
 #pragma unroll
     for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
-    bdf.reltol = a.rtol;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol[i];
-    bdf.reltolQ = 0.0; bdf.abstolQ = 1.0;
     bdf.clear_stats();
     bdf.reinit(a.t0, y0, nullptr);
 
@@ -117,7 +120,7 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
             if (status == SB_SUCCESS) {
                 if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
                 else if (hist && bdf.nst + 1 >= a.hist_cap) status = SB_TOO_MUCH_WORK;
-                else status = bdf.pre_step_checks();
+                else status = bdf.pre_step_checks(sys);
             }
             work = status == SB_SUCCESS;
         }
@@ -127,7 +130,7 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
             const int r = bdf.attempt(sys, mask);
             if (r == SB_SUCCESS) {
                 nloc++;
-                if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
+                if (hist) store_point(hist, bdf.nst, bdf.tn, (int)bdf.qu, bdf.zn[0]);
             } else if (r != SB_TRY_AGAIN) {
                 status = r;
             }
@@ -143,8 +146,8 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
     if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;
-        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
-        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = bdf.nst + 1;
+        s[0] = (int)bdf.st.nst; s[1] = (int)bdf.st.nfe; s[2] = (int)bdf.st.nje; s[3] = (int)bdf.st.nsetups;
+        s[4] = (int)bdf.st.netf; s[5] = (int)bdf.st.ncfn; s[6] = (int)bdf.st.nni; s[7] = bdf.nst + 1;
     }
 }
 
@@ -200,6 +203,16 @@ __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long lo
 
 // ------------------------------------------------------------------------------------ backward
 struct BwdSys {
+    static constexpr bool TSTOP = true;
+    const SbBackwardArgs& a;
+    __device__ __forceinline__ explicit BwdSys(const SbBackwardArgs& a_) : a(a_) {}
+    __device__ __forceinline__ double rtol() const { return a.rtol; }
+    __device__ __forceinline__ double atol(int) const { return a.atol; }
+    __device__ __forceinline__ double rtolQ() const { return a.rtol_q; }
+    __device__ __forceinline__ double atolQ() const { return a.atol_q; }
+    // CVodeB stops the backward integrator at the start of the checkpoint interval, i.e. the
+    // forward problem's initial time; it steps past each t_lower and interpolates back
+    __device__ __forceinline__ double tstop() const { return a.t_end; }
     double p[NP_];
     const double* tab;     // this instance's table base
     int np;                // stored points; intervals are 1 .. np-1
@@ -222,13 +235,13 @@ struct BwdSys {
 #pragma unroll
         for (int k = 0; k < NS; ++k) yi[k] = __ldg(e + 10 + k);
         double c = 1.0;
+        // rolled on purpose: the table lives in memory (dynamic indexing is free there) and the
+        // integrator is instruction-cache bound; this body is inlined at every set_time() site
+#pragma unroll 1
+        for (int i = 0; i < order; ++i) {
+            c *= (t - __ldg(e + 4 + i)) * inv_delt;
 #pragma unroll
-        for (int i = 0; i < SB_QMAX; ++i) {
-            if (i < order) {
-                c *= (t - __ldg(e + 4 + i)) * inv_delt;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) yi[k] = fma(c, __ldg(e + 10 + NS * (i + 1) + k), yi[k]);
-            }
+            for (int k = 0; k < NS; ++k) yi[k] = fma(c, __ldg(e + 10 + NS * (i + 1) + k), yi[k]);
         }
     }
     __device__ __forceinline__ void rhs(const double* lam, double* out) const { sb_adj_rhs(t, yi, lam, p, out); }
@@ -250,7 +263,7 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     if (status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;   // no forward data
 
     Integrator bdf;
-    BwdSys sys;
+    BwdSys sys(a);
     double lam[NS], quad[ND_];
 #pragma unroll
     for (int i = 0; i < NS; ++i) lam[i] = 0.0;
@@ -264,10 +277,6 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     sys.np = np;
     sys.idx = np > 1 ? np - 1 : 1;
     sys.t = 0.0;
-    bdf.reltol = a.rtol;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) bdf.abstol[i] = a.atol;
-    bdf.reltolQ = a.rtol_q; bdf.abstolQ = a.atol_q;
     bdf.reinit(a.t_start, lam, quad);
 
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
@@ -279,9 +288,6 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
             const bool live = valid && status == SB_SUCCESS;
             if (live) {
                 bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
-                // CVodeB stops the backward integrator at the start of the checkpoint interval,
-                // i.e. the forward problem's initial time; it steps past t_lower and interpolates
-                bdf.tstop = a.t_end; bdf.tstopset = true;
                 status = bdf.first_call(sys, t_lower);
             }
             int nloc = 0;
@@ -290,7 +296,7 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
                 bool work = valid && status == SB_SUCCESS && !reached;
                 if (work && !bdf.in_step) {
                     if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
-                    else status = bdf.pre_step_checks();
+                    else status = bdf.pre_step_checks(sys);
                     work = status == SB_SUCCESS;
                 }
                 const unsigned mask = sb_ballot(work);
@@ -299,9 +305,9 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
                     const int r = bdf.attempt(sys, mask);
                     if (r == SB_SUCCESS) {
                         nloc++;
-                        bdf.snap_to_tstop();
+                        bdf.snap_to_tstop(sys);
                         if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
-                        else bdf.limit_to_tstop();
+                        else bdf.limit_to_tstop(sys);
                     } else if (r != SB_TRY_AGAIN) {
                         status = r;
                     }
@@ -332,15 +338,20 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     a.status[inst] = status;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;
-        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
-        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = np;
+        s[0] = (int)bdf.st.nst; s[1] = (int)bdf.st.nfe; s[2] = (int)bdf.st.nje; s[3] = (int)bdf.st.nsetups;
+        s[4] = (int)bdf.st.netf; s[5] = (int)bdf.st.ncfn; s[6] = (int)bdf.st.nni; s[7] = np;
     }
 }
 
 }  // namespace sb
 
+// dynamic shared memory each kernel needs (bytes per block), read by the launcher
+extern "C" __device__ int sb_slab_bytes[2] = {
+    sb::Bdf<SB_NS, 0, sb::FwdSys>::SLAB_SLOTS * SB_BLOCK * 8,
+    sb::Bdf<SB_NS, SB_ND, sb::BwdSys>::SLAB_SLOTS * SB_BLOCK * 8};
+
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
-sb_forward(const SbForwardArgs a) {
+sb_forward(const __grid_constant__ SbForwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     sb::forward_instance(a, inst, inst < a.B);
 }
@@ -354,7 +365,7 @@ sb_tables(const SbTablesArgs a) {
 }
 
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
-sb_backward(const SbBackwardArgs a) {
+sb_backward(const __grid_constant__ SbBackwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     sb::backward_instance(a, inst, inst < a.B);
 }

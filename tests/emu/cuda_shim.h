@@ -14,6 +14,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __grid_constant__
 
 using std::fma; using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::pow;
 using std::max; using std::min; using std::exp; using std::log; using std::log1p; using std::cbrt;
