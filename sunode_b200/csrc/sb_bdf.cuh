@@ -247,39 +247,8 @@ __device__ __forceinline__ void lu_solve(const double* a, const int* piv, double
     }
 }
 
-// ---- per-lane slab in shared memory ---------------------------------------------------------------
-// Resident warps per SM are what hides the FP64 latency of this kernel (measured: throughput grows
-// almost linearly from 2 to 8 warps/SM), and the register file alone holds 8 warps of the
-// integrator.  State that is touched a few times per step -- step-size history, method
-// coefficients, the saved correction, the saved Jacobian, counters -- therefore lives in a
-// per-lane column of shared memory (slot s of lane l at word s * SB_LANES + l: conflict-free), which
-// leaves the registers to the Nordsieck array and the Newton iteration.
-#ifndef SB_HOST_EMULATION
-extern __shared__ double sb_slab_mem[];
-#define SB_LANES SB_BLOCK
-__device__ __forceinline__ double* sb_slab() { return sb_slab_mem + threadIdx.x; }
-#else
-#define SB_LANES 1
-static thread_local double sb_slab_host[2048];
-inline double* sb_slab() { return sb_slab_host; }
-#endif
-template <int OFF> struct SlabArr {          // double array
-    __device__ __forceinline__ double& operator[](int i) const { return sb_slab()[(OFF + i) * SB_LANES]; }
-};
-template <int OFF> struct SlabVal {          // double scalar
-    __device__ __forceinline__ operator double() const { return sb_slab()[OFF * SB_LANES]; }
-    __device__ __forceinline__ double operator=(double v) const { sb_slab()[OFF * SB_LANES] = v; return v; }
-};
-template <int OFF> struct SlabInt {          // int scalar (one slot each)
-    __device__ __forceinline__ int& ref() const { return *reinterpret_cast<int*>(&sb_slab()[OFF * SB_LANES]); }
-    __device__ __forceinline__ operator int() const { return ref(); }
-    __device__ __forceinline__ int operator=(int v) const { ref() = v; return v; }
-    __device__ __forceinline__ int operator++(int) const { return ref()++; }
-};
-
-template <int O> struct Stats {
-    SlabInt<O + 0> nst; SlabInt<O + 1> nfe; SlabInt<O + 2> nje; SlabInt<O + 3> nsetups;
-    SlabInt<O + 4> netf; SlabInt<O + 5> ncfn; SlabInt<O + 6> nni;
+struct Stats {
+    int nst, nfe, nje, nsetups, netf, ncfn, nni;
 };
 
 template <int N, int NQ, class Sys>
@@ -287,41 +256,25 @@ struct Bdf {
     static constexpr int NQ_ = NQ > 0 ? NQ : 1;
     static constexpr bool QUAD = NQ > 0;
 
-    // slab layout (slots of 8 bytes per lane)
-    static constexpr int O_ZSAVE = 0, O_ZSAVEQ = O_ZSAVE + N, O_TAU = O_ZSAVEQ + NQ_,
-                         O_L = O_TAU + SB_LMAX + 1, O_TQ = O_L + SB_LMAX, O_SAVEDJ = O_TQ + 6,
-                         O_SCAL = O_SAVEDJ + N * N, O_INT = O_SCAL + 4, SLAB_SLOTS = O_INT + 10;
-
-    // Nordsieck arrays (registers)
-    double zn[SB_LMAX][N], acor[N], ewt[N];
-    double znQ[SB_LMAX][NQ_], acorQ[NQ_], ewtQ[NQ_];
+    // Nordsieck arrays
+    double zn[SB_LMAX][N], zsave[N], acor[N], ewt[N];
+    double znQ[SB_LMAX][NQ_], zsaveQ[NQ_], acorQ[NQ_], ewtQ[NQ_];
     double ycur[N];                 // zn[0] + acor after the nonlinear solve
-    SlabArr<O_ZSAVE> zsave;         // the correction CVODES parks in zn[qmax]
-    SlabArr<O_ZSAVEQ> zsaveQ;
     // step / order control
-    SlabArr<O_TAU> tau;             // [SB_LMAX + 1]
-    SlabArr<O_L> l;                 // [SB_LMAX]
-    SlabArr<O_TQ> tq;               // [6]
-    double h, hprime, hscale, eta, etamax, tn;
-    double rl1, gamma, gamrat, crate, delp, acnrm;
-    SlabVal<O_SCAL + 0> step_t0;
-    SlabVal<O_SCAL + 1> saved_tq5;
-    SlabVal<O_SCAL + 2> hu;
-    SlabVal<O_SCAL + 3> gammap;
-    int q, qprime, qwait, L;
+    double tau[SB_LMAX + 1], l[SB_LMAX], tq[6];
+    double h, hprime, hscale, eta, etamax, tn, hu;
+    double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+    int q, qprime, qwait, L, qu;
     bool jcur;
     // linear solver
-    SlabArr<O_SAVEDJ> savedJ;       // [N * N], column-major
-    double M[N * N];
+    double savedJ[N * N], M[N * N];
     int piv[N];
     // counters
-    int nst;
-    SlabInt<O_INT + 7> nstlp;
-    SlabInt<O_INT + 8> nstlj;
-    SlabInt<O_INT + 9> qu;
-    Stats<O_INT> st;
+    int nst, nstlp, nstlj;
+    Stats st;
     // a step in flight (cvStep's locals): one call of attempt() is one pass of cvStep's retry loop,
     // so that the lanes of a warp can be re-converged between passes by the caller
+    double step_t0;
     int ncf, nef, nefQ, nflag;
     bool in_step;
     // History manipulations requested by the previous pass (failed pass: restore + rescale, maybe
@@ -350,16 +303,14 @@ struct Bdf {
         q = 1; L = 2; qwait = 2; qprime = 1; etamax = ETAMX1; qu = 0; hu = 0.0;
         nst = 0; nstlp = 0; nstlj = 0;
         saved_tq5 = 0.0; jcur = false; crate = 1.0; delp = 0.0; acnrm = 0.0;
-        h = hprime = hscale = 0.0; eta = 1.0; gamma = gamrat = 1.0; gammap = 1.0; rl1 = 1.0;
+        h = hprime = hscale = 0.0; eta = 1.0; gamma = gammap = gamrat = 1.0; rl1 = 1.0;
         in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL; pend = 0;
     }
 
     __device__ __forceinline__ void clear_stats() {
-        st.nst = 0; st.nfe = 0; st.nje = 0; st.nsetups = 0; st.netf = 0; st.ncfn = 0; st.nni = 0;
+        st.nst = st.nfe = st.nje = st.nsetups = st.netf = st.ncfn = st.nni = 0;
     }
 
-    // tolerances are launch constants: they are read through `sys` (kernel arguments / constant
-    // bank) where they are needed instead of occupying registers
     __device__ __forceinline__ bool set_ewt(const Sys& sys) {
         bool ok = true;
 #pragma unroll
@@ -679,10 +630,9 @@ struct Bdf {
     // ------------------------------------------------------------------ cvSetBDF + cvSetTqBDF
     __device__ __forceinline__ void set_coeffs() {
         double xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0, hsum = h;
-        double lc[SB_LMAX];          // the polynomial is built in registers, then parked in the slab
 #pragma unroll
-        for (int i = 0; i < SB_LMAX; ++i) lc[i] = 0.0;
-        lc[0] = lc[1] = 1.0;
+        for (int i = 0; i < SB_LMAX; ++i) l[i] = 0.0;
+        l[0] = l[1] = 1.0;
         if (q > 1) {
 #pragma unroll
             for (int j = 2; j < SB_QMAX; ++j) {
@@ -692,29 +642,32 @@ struct Bdf {
                     alpha0 -= 1.0 / (double)j;
 #pragma unroll
                     for (int i = SB_QMAX; i >= 1; --i)
-                        if (i <= j) lc[i] = fma(lc[i - 1], xi_inv, lc[i]);
+                        if (i <= j) l[i] = fma(l[i - 1], xi_inv, l[i]);
                 }
             }
             alpha0 -= sb_rk_table[q];
-            xistar_inv = -lc[1] - alpha0;
-            hsum += tau[q - 1];
+            xistar_inv = -l[1] - alpha0;
+            double tau_qm1 = 0.0;
+            static_for<1, SB_LMAX>([&](auto J_) {
+                constexpr int j = SB_IDX(J_);
+                tau_qm1 = (j == q - 1) ? tau[j] : tau_qm1;
+            });
+            hsum += tau_qm1;
             xi_inv = sb_div(h, hsum);
-            alpha0_hat = -lc[1] - xi_inv;
+            alpha0_hat = -l[1] - xi_inv;
 #pragma unroll
             for (int i = SB_QMAX; i >= 1; --i)
-                if (i <= q) lc[i] = fma(lc[i - 1], xistar_inv, lc[i]);
+                if (i <= q) l[i] = fma(l[i - 1], xistar_inv, l[i]);
         }
-        double lq = 1.0;
+        double lq = 1.0, tau_q = 0.0;
         static_for<1, SB_LMAX>([&](auto J_) {
             constexpr int j = SB_IDX(J_);
-            lq = (j == q) ? lc[j] : lq;
+            lq = (j == q) ? l[j] : lq;
+            tau_q = (j == q) ? tau[j] : tau_q;
         });
-#pragma unroll
-        for (int j = 0; j < SB_LMAX; ++j) l[j] = lc[j];
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        const double tq2 = fabs(sb_div(A1, alpha0 * A2));
-        tq[2] = tq2;
+        tq[2] = fabs(sb_div(A1, alpha0 * A2));
         tq[5] = fabs(sb_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
@@ -724,15 +677,15 @@ struct Bdf {
                 const double Cpinv = sb_div(1.0 - A4 + A3, A3);
                 tq[1] = fabs(C * Cpinv);
             } else tq[1] = 1.0;
-            hsum += tau[q];
+            hsum += tau_q;
             xi_inv = sb_div(h, hsum);
             const double A5 = alpha0 - sb_rk_table[q + 1];
             const double A6 = alpha0_hat - xi_inv;
             const double Cppinv = sb_div(1.0 - A6 + A5, A2);
             tq[3] = fabs(sb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq[4] = sb_div(NLSCOEF, tq2);
-        rl1 = sb_div(1.0, lc[1]);
+        tq[4] = sb_div(NLSCOEF, tq[2]);
+        rl1 = sb_div(1.0, l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
         gamrat = (nst > 0) ? sb_div(gamma, gammap) : 1.0;
@@ -747,17 +700,13 @@ struct Bdf {
                           (convfail == FAIL_BAD_J && dgamma < LS_DGMAX) || (convfail == FAIL_OTHER);
         if (jbad) {
             st.nje++; nstlj = nst; jcur = true;
-            sys.jac(ypred, M);
-            if (!all_finite<N * N>(M)) return 1;
-#pragma unroll
-            for (int k = 0; k < N * N; ++k) savedJ[k] = M[k];
+            sys.jac(ypred, savedJ);
+            if (!all_finite<N * N>(savedJ)) return 1;
         } else {
             jcur = false;
-#pragma unroll
-            for (int k = 0; k < N * N; ++k) M[k] = savedJ[k];
         }
 #pragma unroll
-        for (int k = 0; k < N * N; ++k) M[k] = -gamma * M[k];
+        for (int k = 0; k < N * N; ++k) M[k] = -gamma * savedJ[k];
 #pragma unroll
         for (int i = 0; i < N; ++i) M[i + N * i] += 1.0;
         return lu_factor<N>(M, piv) ? 0 : 1;
@@ -852,7 +801,8 @@ struct Bdf {
     __device__ __forceinline__ void complete_step() {
         nst++; st.nst++;
         hu = h; qu = q;
-        for (int i = q; i >= 2; --i) tau[i] = tau[i - 1];
+#pragma unroll
+        for (int i = SB_QMAX; i >= 2; --i) tau[i] = (i <= q) ? tau[i - 1] : tau[i];
         if (q == 1 && nst > 1) tau[2] = tau[1];
         tau[1] = h;
         // l[j] == 0 and zn[j] == 0 for j > q, so the update runs over all rows

@@ -13,14 +13,15 @@
 // communication at all.  Inputs/outputs are instance-major (a batch-1 view is byte-compatible
 // with the reference's [n_t, n_s] C-order buffers).
 #pragma once
+#include "sb_args.h"
+#include "sb_bdf.cuh"
+
 #ifndef SB_BLOCK
-#define SB_BLOCK 32
+#define SB_BLOCK 128
 #endif
 #ifndef SB_MIN_BLOCKS
 #define SB_MIN_BLOCKS 1
 #endif
-#include "sb_args.h"
-#include "sb_bdf.cuh"
 
 namespace sb {
 
@@ -41,6 +42,8 @@ struct FwdSys {
     double p[NP_];
     double t;
     __device__ __forceinline__ explicit FwdSys(const SbForwardArgs& a_) : a(a_) {}
+    // tolerances / stop time are launch constants: read from the kernel arguments (constant
+    // bank) where needed instead of being carried in registers
     __device__ __forceinline__ double rtol() const { return a.rtol; }
     __device__ __forceinline__ double atol(int i) const { return __ldg(a.atol + i); }
     __device__ __forceinline__ double rtolQ() const { return 0.0; }
@@ -130,7 +133,7 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
             const int r = bdf.attempt(sys, mask);
             if (r == SB_SUCCESS) {
                 nloc++;
-                if (hist) store_point(hist, bdf.nst, bdf.tn, (int)bdf.qu, bdf.zn[0]);
+                if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
             } else if (r != SB_TRY_AGAIN) {
                 status = r;
             }
@@ -146,8 +149,8 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
     if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;
-        s[0] = (int)bdf.st.nst; s[1] = (int)bdf.st.nfe; s[2] = (int)bdf.st.nje; s[3] = (int)bdf.st.nsetups;
-        s[4] = (int)bdf.st.netf; s[5] = (int)bdf.st.ncfn; s[6] = (int)bdf.st.nni; s[7] = bdf.nst + 1;
+        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = bdf.nst + 1;
     }
 }
 
@@ -338,17 +341,12 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     a.status[inst] = status;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;
-        s[0] = (int)bdf.st.nst; s[1] = (int)bdf.st.nfe; s[2] = (int)bdf.st.nje; s[3] = (int)bdf.st.nsetups;
-        s[4] = (int)bdf.st.netf; s[5] = (int)bdf.st.ncfn; s[6] = (int)bdf.st.nni; s[7] = np;
+        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = np;
     }
 }
 
 }  // namespace sb
-
-// dynamic shared memory each kernel needs (bytes per block), read by the launcher
-extern "C" __device__ int sb_slab_bytes[2] = {
-    sb::Bdf<SB_NS, 0, sb::FwdSys>::SLAB_SLOTS * SB_BLOCK * 8,
-    sb::Bdf<SB_NS, SB_ND, sb::BwdSys>::SLAB_SLOTS * SB_BLOCK * 8};
 
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {

@@ -50,16 +50,17 @@ def _ip(a):
 
 
 class Emulator:
-    def __init__(self, problem, workdir):
+    def __init__(self, problem, workdir, defines=()):
         gen = problem.generated
         self.ns, self.np, self.nd = gen.n_states, gen.n_params, gen.n_deriv
         os.makedirs(workdir, exist_ok=True)
         inc = os.path.join(workdir, 'generated_problem.inc')
         with open(inc, 'w') as fh:
             fh.write(gen.cuda)
-        out = os.path.join(workdir, 'emu_%s.so' % gen.digest)
+        out = os.path.join(workdir, 'emu_%s%s.so' % (gen.digest, ''.join('_' + d.replace('=', '') for d in defines)))
         cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
         cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off',
+               *['-D' + d for d in defines],
                '-I', workdir, '-I', _HERE, '-I', _CSRC, os.path.join(_HERE, 'emu_main.cpp'),
                '-o', out]
         proc = subprocess.run(cmd, capture_output=True, text=True)
