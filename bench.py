@@ -371,10 +371,16 @@ def main():
     dom_ms = float(kern_ms[:, dom].mean())
     achieved = bytes_solve * B / (dom_ms * 1e-3) / 1e9
     info = eng.kernel_info()
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get('%s:%d:%s' % (w.name, B, 'sb_backward' if w.adjoint else 'sb_forward'))
     roofline = {
         'bound': 'hbm', 'kernel': 'sb_backward' if w.adjoint else 'sb_forward',
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-        'traffic': None, 'peak_source': peak_src,
+        'traffic': traffic, 'traffic_source': 'ncu --set full capture, profiles/ncu_traffic.json' if traffic else None,
+        'peak_source': peak_src,
         'algorithmic_bytes_per_solve': bytes_solve, 'kernel_ms': dom_ms,
         'kernel_ms_all': {'sb_forward': float(kern_ms[:, 0].mean()),
                           'sb_tables': float(kern_ms[:, 1].mean()),
