@@ -85,6 +85,16 @@ int sb_solve_forward(sb_problem* p, int64_t B, double t0, const double* tvals, i
                      const double* y0, const double* params, double* y_out, int32_t* status,
                      int32_t* stats, int store_history, int mem, void* stream);
 
+/* Solver.solve with forward sensitivities (Solver(sens_mode=...), solver.py:360-392, 483-527):
+ * y and the n_deriv sensitivity vectors dy/dp_k are integrated together (CVODES simultaneous
+ * corrector, sensitivity error control on, analytic sensitivity right-hand side).
+ *   sens0[B][n_deriv][n_states] (or [n_deriv][n_states] if sens0_shared),
+ *   sens_out[B][n_t][n_deriv][n_states]  (the reference's sens_out[n_t, n_params, n_states]). */
+int sb_solve_forward_sens(sb_problem* p, int64_t B, double t0, const double* tvals, int n_t,
+                          const double* y0, const double* params, const double* sens0,
+                          int sens0_shared, double* y_out, double* sens_out, int32_t* status,
+                          int32_t* stats, int mem, void* stream);
+
 /* AdjointSolver.solve_backward (solver.py:723-784), batched, on the history stored by the last
  * sb_solve_forward(store_history = 1) of this handle (same B, n_t, tvals).
  *   t_start = the reference's `t0` argument (the LAST time), t_end = `tend` (the initial time);

@@ -38,7 +38,7 @@
 #include <omp.h>
 #endif
 
-#define NMAX 24          /* max states / quadratures handled by the oracle */
+#define NMAX 96          /* max length of the (stacked) state vector / quadratures handled by the oracle */
 #define QMAX 5
 #define LMAX (QMAX + 1)
 
@@ -121,6 +121,7 @@ typedef struct {
     fn4_t adj_rhs;   /* -J^T lam */
     fn3_t adj_jac;   /* column-major -J^T */
     fn4_t quad_rhs;  /* lam^T df/dp */
+    fn4_t sens_rhs;  /* (t, y, s[nd][ns], p, out[nd][ns]): J s_k + df/dp_k (may be NULL) */
 } oracle_problem;
 
 /* ---- adjoint data store ---------------------------------------------------------------------- */
@@ -147,6 +148,11 @@ typedef int (*sys_quad_t)(struct cv_mem*, double t, const double* y, double* qdo
 
 typedef struct cv_mem {
     int N, NQ;
+    /* forward sensitivity analysis (CV_SIMULTANEOUS, sensitivity error control on;
+     * /root/reference/sunode/solver.py:360-392): y and the sensitivity vectors are stacked,
+     * N = NM * nblk; all blocks share h, q and the iteration matrix (dimension NM); norms are the
+     * max over the per-block WRMS norms.  nblk = 1: plain problem (NM == N). */
+    int NM, nblk;
     sys_rhs_t f;
     sys_jac_t jacfn;
     sys_quad_t fQ;
@@ -173,7 +179,7 @@ typedef struct cv_mem {
     long nst, nfe, nfQe, ncfn, netf, netfQ, nni, nsetups, nje, nstlp, nstlj, nhnil;
     int jcur, forceSetup, convfail;
 
-    double savedJ[NMAX * NMAX], M[NMAX * NMAX];
+    double savedJ[24 * 24], M[24 * 24];
     int piv[NMAX];
 } cv_mem;
 
@@ -182,6 +188,16 @@ static double wrms(const double* v, const double* w, int n) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) { double x = v[i] * w[i]; s += x * x; }
     return sqrt(s / n);
+}
+
+/* max over blocks of the WRMS norm (N_VWrmsNorm of CVODES' sensitivity wrapper vector) */
+static double vnorm(const cv_mem* m, const double* v, const double* w) {
+    double r = 0.0;
+    for (int b = 0; b < m->nblk; ++b) {
+        double x = wrms(v + b * m->NM, w + b * m->NM, m->NM);
+        if (b == 0 || x > r) r = x;
+    }
+    return r;
 }
 
 static int ewt_set(cv_mem* m, const double* ycur, double* w) {
@@ -280,7 +296,7 @@ static int ydd_norm(cv_mem* m, double hg, double* yddnrm) {
         if (r > 0) return QRHSFUNC_RECVR;
     }
     for (int i = 0; i < m->N; ++i) m->tempv[i] = (m->tempv[i] - m->zn[1][i]) / hg;
-    *yddnrm = wrms(m->tempv, m->ewt, m->N);
+    *yddnrm = vnorm(m, m->tempv, m->ewt);
     if (m->quadr && m->errconQ) {
         for (int i = 0; i < m->NQ; ++i) m->tempvQ[i] = (m->tempvQ[i] - m->znQ[1][i]) / hg;
         double nq = wrms(m->tempvQ, m->ewtQ, m->NQ);
@@ -475,7 +491,7 @@ static void cv_set(cv_mem* m) {
 
 /* ---- linear solver setup (cvLsSetup with dense matrix + analytic Jacobian) --------------------- */
 static int ls_setup(cv_mem* m, int convfail, const double* ypred) {
-    int n = m->N;
+    int n = m->NM;
     double dgamma = fabs((m->gamma / m->gammap) - 1.0);
     int jbad = (m->nst == 0) || (m->nst > m->nstlj + MSBJ) ||
                ((convfail == FAIL_BAD_J) && (dgamma < CVLS_DGMAX)) || (convfail == FAIL_OTHER);
@@ -528,16 +544,16 @@ static int cv_nls(cv_mem* m, int nflag) {
         for (;;) {
             m->nni++;
             for (int i = 0; i < n; ++i) delta[i] = -delta[i];
-            lu_solve(m->M, n, m->piv, delta);
+            for (int b = 0; b < m->nblk; ++b) lu_solve(m->M, m->NM, m->piv, delta + b * m->NM);
             if (m->gamrat != 1.0) { double s = 2.0 / (1.0 + m->gamrat); for (int i = 0; i < n; ++i) delta[i] *= s; }
             for (int i = 0; i < n; ++i) m->acor[i] += delta[i];
 
             /* convergence test */
-            double del = wrms(delta, m->ewt, n);
+            double del = vnorm(m, delta, m->ewt);
             if (curiter > 0) m->crate = fmax(CRDOWN * m->crate, del / m->delp);
             double dcon = del * fmin(1.0, m->crate) / m->tq[4];
             if (dcon <= 1.0) {
-                m->acnrm = (curiter == 0) ? del : wrms(m->acor, m->ewt, n);
+                m->acnrm = (curiter == 0) ? del : vnorm(m, m->acor, m->ewt);
                 m->jcur = 0;
                 for (int i = 0; i < n; ++i) m->y[i] = m->zn[0][i] + m->acor[i];
                 return CV_SUCCESS;
@@ -666,7 +682,7 @@ static void cv_prepare_next_step(cv_mem* m, double dsm) {
     /* eta at order q-1 */
     m->etaqm1 = 0.0;
     if (m->q > 1) {
-        double ddn = wrms(m->zn[m->q], m->ewt, m->N);
+        double ddn = vnorm(m, m->zn[m->q], m->ewt);
         if (m->quadr && m->errconQ) { double dq = wrms(m->znQ[m->q], m->ewtQ, m->NQ); if (dq > ddn) ddn = dq; }
         ddn *= m->tq[1];
         m->etaqm1 = 1.0 / (pow(BIAS1 * ddn, 1.0 / m->q) + ADDON);
@@ -676,7 +692,7 @@ static void cv_prepare_next_step(cv_mem* m, double dsm) {
     if (m->q != QMAX && m->saved_tq5 != 0.0) {
         double cquot = (m->tq[5] / m->saved_tq5) * pow(m->h / m->tau[2], (double)m->L);
         for (int i = 0; i < m->N; ++i) m->tempv[i] = m->acor[i] - cquot * m->zn[QMAX][i];
-        double dup = wrms(m->tempv, m->ewt, m->N);
+        double dup = vnorm(m, m->tempv, m->ewt);
         if (m->quadr && m->errconQ) {
             for (int i = 0; i < m->NQ; ++i) m->tempvQ[i] = m->acorQ[i] - cquot * m->znQ[QMAX][i];
             double dq = wrms(m->tempvQ, m->ewtQ, m->NQ); if (dq > dup) dup = dq;
@@ -851,7 +867,7 @@ static int cv_solve(cv_mem* m, double tout, double* yout, double* tret, int itas
             for (int i = 0; i < m->N; ++i) yout[i] = m->zn[0][i];
             break;
         }
-        double nrm = wrms(m->zn[0], m->ewt, m->N);
+        double nrm = vnorm(m, m->zn[0], m->ewt);
         if (m->quadr && m->errconQ) { double nq = wrms(m->znQ[0], m->ewtQ, m->NQ); if (nq > nrm) nrm = nq; }
         m->tolsf = UROUND * nrm;
         if (m->tolsf > 1.0) {
@@ -1033,7 +1049,7 @@ typedef struct {
 
 static void set_fwd_tols(cv_mem* m, const oracle_options* o) {
     m->reltol = o->rtol;
-    for (int i = 0; i < m->N; ++i) m->abstol[i] = (o->n_atol == 1) ? o->atol[0] : o->atol[i];
+    for (int i = 0; i < m->N; ++i) m->abstol[i] = (o->n_atol == 1) ? o->atol[0] : o->atol[i % m->NM];
 }
 
 /* stats layout: nst, nfe, nje, nsetups, netf, ncfn, nni, (bwd) nst, nfe, nje, nsetups, netf(+Q), ncfn, nni */
@@ -1045,7 +1061,7 @@ int oracle_solve_forward(const oracle_problem* prob, const oracle_options* opt,
                          const double* p, double* y_out, long* stats)
 {
     cv_mem m; memset(&m, 0, sizeof(m));
-    m.N = prob->ns; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
+    m.N = prob->ns; m.NM = prob->ns; m.nblk = 1; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
     set_fwd_tols(&m, opt);
     m.mxstep = opt->mxstep;
     cv_reinit(&m, t0, y0);
@@ -1073,7 +1089,7 @@ static int adjoint_forward(const oracle_problem* prob, const oracle_options* opt
                            double* y_out, hist_t* H, long* stats)
 {
     cv_mem m; memset(&m, 0, sizeof(m));
-    m.N = prob->ns; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
+    m.N = prob->ns; m.NM = prob->ns; m.nblk = 1; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
     set_fwd_tols(&m, opt);
     m.mxstep = opt->mxstep;
     cv_reinit(&m, t0, y0);
@@ -1119,7 +1135,7 @@ static int adjoint_backward(const oracle_problem* prob, const oracle_options* op
 {
     int ns = prob->ns, nd = prob->nd;
     cv_mem m; memset(&m, 0, sizeof(m));
-    m.N = ns; m.NQ = nd; m.f = bwd_rhs; m.jacfn = bwd_jac; m.fQ = bwd_quad; m.prob = prob; m.p = p;
+    m.N = ns; m.NM = ns; m.nblk = 1; m.NQ = nd; m.f = bwd_rhs; m.jacfn = bwd_jac; m.fQ = bwd_quad; m.prob = prob; m.p = p;
     m.hist = H;
     m.reltol = opt->rtol_b; for (int i = 0; i < ns; ++i) m.abstol[i] = opt->atol_b;
     m.reltolQ = opt->rtol_q; m.abstolQ = opt->atol_q;
@@ -1168,6 +1184,80 @@ static int adjoint_backward(const oracle_problem* prob, const oracle_options* op
 }
 
 static void hist_free(hist_t* H) { free(H->t); free(H->y); free(H->order); }
+
+/* ---- forward sensitivities: Solver(sens_mode=...).solve (solver.py:467-527 with 483-488, 523-527)
+ * y_out[n_t][ns], sens_out[n_t][nd][ns]; sens0[nd][ns]. */
+static int fsa_rhs(cv_mem* m, double t, const double* y, double* ydot) {
+    int ns = m->NM;
+    int r = m->prob->rhs(t, y, m->p, ydot);
+    if (r) return r;
+    return m->prob->sens_rhs(t, y, y + ns, m->p, ydot + ns);
+}
+
+int oracle_solve_forward_sens(const oracle_problem* prob, const oracle_options* opt,
+                              double t0, const double* tvals, int n_t, const double* y0,
+                              const double* p, const double* sens0, double* y_out,
+                              double* sens_out, long* stats)
+{
+    int ns = prob->ns, nd = prob->nd, nt = ns * (1 + nd);
+    if (nt > NMAX || !prob->sens_rhs) return CV_ILL_INPUT;
+    cv_mem m; memset(&m, 0, sizeof(m));
+    m.N = nt; m.NM = ns; m.nblk = 1 + nd; m.NQ = 0; m.f = fsa_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
+    set_fwd_tols(&m, opt);
+    m.mxstep = opt->mxstep;
+    double yy[NMAX];
+    memcpy(yy, y0, sizeof(double) * ns);
+    memcpy(yy + ns, sens0, sizeof(double) * ns * nd);
+    cv_reinit(&m, t0, yy);
+    int status = 0;
+    double tret = t0, ybuf[NMAX];
+    for (int i = 0; i < n_t; ++i) {
+        if (tvals[i] == t0) {               /* row 0, solver.py:505-508 */
+            memcpy(y_out, y0, sizeof(double) * ns);
+            memcpy(sens_out, sens0, sizeof(double) * ns * nd);
+            continue;
+        }
+        int ok = 0;
+        for (int retry = 0; retry < opt->max_retries; ++retry) {
+            int r = cv_solve(&m, tvals[i], ybuf, &tret, CV_NORMAL);
+            if (r == 0) { ok = 1; break; }
+            if (r != CV_TOO_MUCH_WORK) { status = r; break; }
+        }
+        if (status) break;
+        if (!ok) { status = CV_TOO_MUCH_WORK; break; }
+        memcpy(y_out + (size_t)i * ns, ybuf, sizeof(double) * ns);
+        memcpy(sens_out + (size_t)i * ns * nd, ybuf + ns, sizeof(double) * ns * nd);
+    }
+    if (stats) { stats[0] = m.nst; stats[1] = m.nfe; stats[2] = m.nje; stats[3] = m.nsetups; stats[4] = m.netf; stats[5] = m.ncfn; stats[6] = m.nni; }
+    return status;
+}
+
+int oracle_solve_forward_sens_batch(const oracle_problem* prob, const oracle_options* opt, long B,
+                                    double t0, const double* tvals, int n_t, const double* y0,
+                                    const double* p, const double* sens0, int sens0_shared,
+                                    double* y_out, double* sens_out, int* status, long* stats,
+                                    int n_threads)
+{
+    int ns = prob->ns, np_ = prob->np, nd = prob->nd;
+#ifdef _OPENMP
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());
+#endif
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long b = 0; b < B; ++b) {
+        long st[16] = {0};
+        const double* s0 = sens0_shared ? sens0 : sens0 + (size_t)b * nd * ns;
+        int r = oracle_solve_forward_sens(prob, opt, t0, tvals, n_t, y0 + b * ns, p + b * np_, s0,
+                                          y_out + (size_t)b * n_t * ns,
+                                          sens_out + (size_t)b * n_t * nd * ns, st);
+        if (r) {
+            for (size_t k = 0; k < (size_t)n_t * ns; ++k) y_out[(size_t)b * n_t * ns + k] = NAN;
+            for (size_t k = 0; k < (size_t)n_t * nd * ns; ++k) sens_out[(size_t)b * n_t * nd * ns + k] = NAN;
+        }
+        if (status) status[b] = r;
+        if (stats) memcpy(stats + b * 16, st, sizeof(st));
+    }
+    return 0;
+}
 
 /* One forward + one backward solve (the notebook's unit of work, from_sympy.ipynb:178-179). */
 int oracle_solve_adjoint(const oracle_problem* prob, const oracle_options* opt, double t0,

@@ -30,7 +30,8 @@ _LP = ctypes.POINTER(ctypes.c_long)
 class _Problem(ctypes.Structure):
     _fields_ = [('ns', ctypes.c_int), ('np', ctypes.c_int), ('nd', ctypes.c_int),
                 ('rhs', ctypes.c_void_p), ('jac', ctypes.c_void_p), ('adj_rhs', ctypes.c_void_p),
-                ('adj_jac', ctypes.c_void_p), ('quad_rhs', ctypes.c_void_p)]
+                ('adj_jac', ctypes.c_void_p), ('quad_rhs', ctypes.c_void_p),
+                ('sens_rhs', ctypes.c_void_p)]
 
 
 class _Options(ctypes.Structure):
@@ -91,7 +92,7 @@ class Oracle:
             return ctypes.cast(getattr(clib, prefix + name), ctypes.c_void_p).value
 
         self._prob = _Problem(ns, npar, nd, addr('rhs'), addr('jac'), addr('adj_rhs'),
-                              addr('adj_jac'), addr('quad_rhs'))
+                              addr('adj_jac'), addr('quad_rhs'), addr('sens_rhs'))
         atol_arr = np.atleast_1d(np.asarray(atol, dtype=np.float64)).copy()
         if atol_arr.size not in (1, ns):
             raise ValueError('atol must be a scalar or have one entry per state')
@@ -130,6 +131,26 @@ class Oracle:
             ctypes.c_double(t0), _dp(tvals), ctypes.c_int(n_t), _dp(y0), _dp(params), _dp(y_out),
             status.ctypes.data_as(_IP), stats.ctypes.data_as(_LP), ctypes.c_int(n_threads))
         return y_out, status, stats
+
+    def solve_forward_sens(self, t0, tvals, y0, params, sens0, n_threads=0):
+        """Batched ``Solver(sens_mode=...).solve``.  ``sens0`` is ``[nd, ns]`` (shared) or
+        ``[B, nd, ns]``.  Returns (y_out[B, n_t, ns], sens_out[B, n_t, nd, ns], status, stats)."""
+        tvals = np.ascontiguousarray(tvals, dtype=np.float64)
+        y0, params, B = self._prep(y0, params)
+        n_t = len(tvals)
+        sens0 = np.ascontiguousarray(sens0, dtype=np.float64)
+        shared = int(sens0.ndim == 2)
+        assert sens0.shape[-2:] == (self.nd, self.ns)
+        y_out = np.zeros((B, n_t, self.ns))
+        sens_out = np.zeros((B, n_t, self.nd, self.ns))
+        status = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, NSTATS), dtype=np.int64)
+        lib().oracle_solve_forward_sens_batch(
+            ctypes.byref(self._prob), ctypes.byref(self._opt), ctypes.c_long(B),
+            ctypes.c_double(t0), _dp(tvals), ctypes.c_int(n_t), _dp(y0), _dp(params), _dp(sens0),
+            ctypes.c_int(shared), _dp(y_out), _dp(sens_out), status.ctypes.data_as(_IP),
+            stats.ctypes.data_as(_LP), ctypes.c_int(n_threads))
+        return y_out, sens_out, status, stats
 
     def solve_adjoint(self, t0, tvals, y0, params, grads, n_threads=0):
         """Batched ``solve_forward`` + ``solve_backward(tvals[-1], t0, tvals, grads, ...)``.

@@ -197,6 +197,25 @@ class Engine:
             self._h, B, float(t0), tvals.ctypes.data, n_t, a_y0.ptr, a_p.ptr, a_out.ptr, a_st.ptr,
             a_stats.ptr, int(bool(store_history)), mem, _stream(mem, stream)))
 
+    def forward_sens(self, t0: float, tvals, y0, params, sens0, y_out, sens_out, status, stats=None,
+                     *, stream: Optional[int] = None) -> None:
+        tvals = np.ascontiguousarray(tvals, dtype=np.float64)
+        n_t = int(tvals.shape[0])
+        B = int(y0.shape[0])
+        shared = int(len(sens0.shape) == 2)
+        a_y0 = _arg(y0, (B, self.ns), 'y0')
+        a_p = _arg(params, (B, self.np), 'params')
+        a_s0 = _arg(sens0, (self.nd, self.ns) if shared else (B, self.nd, self.ns), 'sens0')
+        a_out = _arg(y_out, (B, n_t, self.ns), 'y_out', writable=True)
+        a_so = _arg(sens_out, (B, n_t, self.nd, self.ns), 'sens_out', writable=True)
+        a_st = _arg(status, (B,), 'status', dtype=np.int32, writable=True)
+        a_stats = _arg(stats, (B, _lib.SB_STATS_PER_INSTANCE), 'stats', dtype=np.int32,
+                       writable=True, optional=True)
+        mem = _mem_kind([a_y0, a_p, a_s0, a_out, a_so, a_st, a_stats])
+        _lib.check(self._lib.sb_solve_forward_sens(
+            self._h, B, float(t0), tvals.ctypes.data, n_t, a_y0.ptr, a_p.ptr, a_s0.ptr, shared,
+            a_out.ptr, a_so.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream)))
+
     def backward(self, t_start: float, t_end: float, tvals, params, grads, grad_out, lamda_out,
                  status, stats=None, *, stream: Optional[int] = None) -> None:
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)

@@ -27,7 +27,10 @@ typedef struct SbForwardArgs {
     int n_t;
     int hist_cap;
     int max_steps;            /* internal steps allowed per output time */
-    int pad_;
+    int sens0_shared;         /* sens0 is [ND][NS] for all instances instead of [B][ND][NS] */
+    /* forward sensitivities (sb_forward_sens only; NULL otherwise) */
+    const double* sens0;      /* [B][ND][NS] or [ND][NS] */
+    double* sens_out;         /* [B][n_t][ND][NS] */
 } SbForwardArgs;
 
 typedef struct SbTablesArgs {

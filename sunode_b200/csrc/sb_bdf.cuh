@@ -251,10 +251,25 @@ struct Stats {
     int nst, nfe, nje, nsetups, netf, ncfn, nni;
 };
 
-template <int N, int NQ, class Sys>
+// NM = dimension of the ODE (and of the Newton matrix), NBLK = number of NM-sized blocks that are
+// integrated together: 1 for a plain solve, 1 + n_sens for CVODES' simultaneous forward
+// sensitivity analysis, where block 0 is y and block 1 + k the sensitivity dy/dp_k.  All blocks
+// share the step size, the order and the iteration matrix I - gamma*J; norms are the maximum of
+// the per-block WRMS norms (sensitivity error control on, as the reference sets it,
+// /root/reference/sunode/solver.py:391-392).  NQ quadrature variables ride along (adjoint only).
+template <int NM, int NQ, class Sys, int NBLK = 1>
 struct Bdf {
+    static constexpr int N = NM * NBLK;          // total length of the state vector
     static constexpr int NQ_ = NQ > 0 ? NQ : 1;
     static constexpr bool QUAD = NQ > 0;
+
+    // max over blocks of the weighted RMS norm (one block: the plain WRMS norm)
+    __device__ __forceinline__ double norm(const double* v) const {
+        double r = wrms<NM>(v, ewt);
+#pragma unroll
+        for (int b = 1; b < NBLK; ++b) r = fmax(r, wrms<NM>(v + b * NM, ewt + b * NM));
+        return r;
+    }
 
     // Nordsieck arrays
     double zn[SB_LMAX][N], zsave[N], acor[N], ewt[N];
@@ -267,8 +282,8 @@ struct Bdf {
     int q, qprime, qwait, L, qu;
     bool jcur;
     // linear solver
-    double savedJ[N * N], M[N * N];
-    int piv[N];
+    double savedJ[NM * NM], M[NM * NM];
+    int piv[NM];
     // counters
     int nst, nstlp, nstlj;
     Stats st;
@@ -315,7 +330,7 @@ struct Bdf {
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double d = fma(sys.rtol(), fabs(zn[0][i]), sys.atol(i));
+            const double d = fma(sys.rtol(), fabs(zn[0][i]), sys.atol(i % NM));
             ok = ok && (d > 0.0);
             ewt[i] = sb_div(1.0, d);
         }
@@ -341,7 +356,7 @@ struct Bdf {
         const double rhg = sb_div(1.0, hg);
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = (f[i] - zn[1][i]) * rhg;
-        double nrm = wrms<N>(f, ewt);
+        double nrm = norm(f);
         if (QUAD) {
             double fq[NQ_];
             sys.quad(y, fq);
@@ -701,15 +716,15 @@ struct Bdf {
         if (jbad) {
             st.nje++; nstlj = nst; jcur = true;
             sys.jac(ypred, savedJ);
-            if (!all_finite<N * N>(savedJ)) return 1;
+            if (!all_finite<NM * NM>(savedJ)) return 1;
         } else {
             jcur = false;
         }
 #pragma unroll
-        for (int k = 0; k < N * N; ++k) M[k] = -gamma * savedJ[k];
+        for (int k = 0; k < NM * NM; ++k) M[k] = -gamma * savedJ[k];
 #pragma unroll
-        for (int i = 0; i < N; ++i) M[i + N * i] += 1.0;
-        return lu_factor<N>(M, piv) ? 0 : 1;
+        for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
+        return lu_factor<NM>(M, piv) ? 0 : 1;
     }
 
     // ------------------------------------------------------------------ nonlinear solve
@@ -752,7 +767,8 @@ struct Bdf {
             for (int m = 0; m < NLS_MAXCOR; ++m) {
                 if (run) {
                     st.nni++;
-                    lu_solve<N>(M, piv, delta);
+#pragma unroll
+                    for (int b = 0; b < NBLK; ++b) lu_solve<NM>(M, piv, delta + b * NM);
                     if (gamrat != 1.0) {
                         const double sc = sb_div(2.0, 1.0 + gamrat);
 #pragma unroll
@@ -760,11 +776,11 @@ struct Bdf {
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) { acor[i] += delta[i]; ycur[i] = zn[0][i] + acor[i]; }
-                    const double del = wrms<N>(delta, ewt);
+                    const double del = norm(delta);
                     if (m > 0) crate = fmax(CRDOWN * crate, sb_div(del, delp));
                     const double dcon = sb_div(del * fmin(1.0, crate), tq[4]);
                     if (dcon <= 1.0) {
-                        acnrm = (m == 0) ? del : wrms<N>(acor, ewt);
+                        acnrm = (m == 0) ? del : norm(acor);
                         jcur = false;
                         retval = 0; done = true; run = false;
                     } else if (!(dcon > 1.0)) {                       // NaN
@@ -856,7 +872,7 @@ struct Bdf {
 #pragma unroll
                 for (int i = 0; i < NQ_; ++i) zqQ[i] = is_q ? znQ[j][i] : zqQ[i];
             });
-            double ddn = wrms<N>(zq, ewt);
+            double ddn = norm(zq);
             if (QUAD) ddn = fmax(ddn, wrms<NQ_>(zqQ, ewtQ));
             ddn *= tq[1];
             etaqm1 = sb_div(1.0, root_k(BIAS1 * ddn, q) + ADDON);
@@ -870,7 +886,7 @@ struct Bdf {
             double tmp[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) tmp[i] = fma(-cquot, zsave[i], acor[i]);
-            double dup = wrms<N>(tmp, ewt);
+            double dup = norm(tmp);
             if (QUAD) {
                 double tmpq[NQ_];
 #pragma unroll
@@ -1044,7 +1060,7 @@ struct Bdf {
     // Per-step bookkeeping CVode() does around cvStep for nst > 0.  Returns <0 on failure.
     __device__ __forceinline__ int pre_step_checks(const Sys& sys) {
         if (nst > 0 && !set_ewt(sys)) return SB_ILL_INPUT;
-        double nrm = wrms<N>(zn[0], ewt);
+        double nrm = norm(zn[0]);
         if (QUAD) nrm = fmax(nrm, wrms<NQ_>(znQ[0], ewtQ));
         if (SB_UROUND * nrm > 1.0) return SB_TOO_MUCH_ACC;
         return SB_SUCCESS;

@@ -36,12 +36,16 @@ constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // ------------------------------------------------------------------------------------ forward
-struct FwdSys {
+// NBLK = 1: plain forward problem.  NBLK = 1 + ND: y and the ND sensitivity vectors dy/dp_k stacked
+// (CVODES forward sensitivity analysis, /root/reference/sunode/solver.py:360-392 with the
+// analytic sensitivity right-hand side J s_k + df/dp_k of symode/problem.py:557-583).
+template <int NBLK>
+struct FwdSysT {
     static constexpr bool TSTOP = false;
     const SbForwardArgs& a;
     double p[NP_];
     double t;
-    __device__ __forceinline__ explicit FwdSys(const SbForwardArgs& a_) : a(a_) {}
+    __device__ __forceinline__ explicit FwdSysT(const SbForwardArgs& a_) : a(a_) {}
     // tolerances / stop time are launch constants: read from the kernel arguments (constant
     // bank) where needed instead of being carried in registers
     __device__ __forceinline__ double rtol() const { return a.rtol; }
@@ -50,10 +54,14 @@ struct FwdSys {
     __device__ __forceinline__ double atolQ() const { return 1.0; }
     __device__ __forceinline__ double tstop() const { return 0.0; }
     __device__ __forceinline__ void set_time(double t_) { t = t_; }
-    __device__ __forceinline__ void rhs(const double* y, double* out) const { sb_rhs(t, y, p, out); }
+    __device__ __forceinline__ void rhs(const double* y, double* out) const {
+        sb_rhs(t, y, p, out);
+        if (NBLK > 1) sb_sens_rhs(t, y, y + NS, p, out + NS);
+    }
     __device__ __forceinline__ void jac(const double* y, double* J) const { sb_jac(t, y, p, J); }
     __device__ __forceinline__ void quad(const double*, double*) const {}
 };
+using FwdSys = FwdSysT<1>;
 
 __device__ __forceinline__ void store_point(double* hist, int idx, double t, int order, const double* y) {
     double* e = hist + (size_t)idx * HIST_STRIDE;
@@ -72,20 +80,29 @@ __device__ __forceinline__ void store_point(double* hist, int idx, double t, int
 // Forward: the k-loop over output times of the reference (solver.py:503-521, 705-721) is flattened
 // into the step loop -- a lane emits every output time it has already stepped past and then
 // takes its next step -- so that lanes do not wait for each other at every output time.
-__device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst, bool valid) {
-    using Integrator = Bdf<NS, 0, FwdSys>;
+template <int NBLK>
+__device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long long inst, bool valid) {
+    using Sys = FwdSysT<NBLK>;
+    using Integrator = Bdf<NS, 0, Sys, NBLK>;
+    constexpr int NT = NS * NBLK;
     Integrator bdf;
-    FwdSys sys(a);
-    double y0[NS];
+    Sys sys(a);
+    double y0[NT];
     if (!valid) inst = 0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) y0[i] = a.y0[inst * NS + i];
+    if (NBLK > 1) {
+        const double* s0 = a.sens0_shared ? a.sens0 : a.sens0 + (size_t)inst * (NT - NS);
+#pragma unroll
+        for (int i = NS; i < NT; ++i) y0[i] = s0[i - NS];
+    }
 #pragma unroll
     for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
     bdf.clear_stats();
     bdf.reinit(a.t0, y0, nullptr);
 
     double* yo = a.y_out + (size_t)inst * a.n_t * NS;
+    double* so = (NBLK > 1) ? a.sens_out + (size_t)inst * a.n_t * (NT - NS) : nullptr;
     double* hist = a.hist ? a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE : nullptr;
     int status = SB_SUCCESS;
     int k = 0;          // next output time
@@ -99,14 +116,18 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
             for (;;) {
                 const double tout = a.tvals[k];
                 if (tout == a.t0) {
-                    // the reference writes row 0 here whatever k is (solver.py:505,707)
+                    // the reference writes row 0 here whatever k is (solver.py:505-508,707)
 #pragma unroll
                     for (int i = 0; i < NS; ++i) yo[i] = y0[i];
+#pragma unroll
+                    for (int i = NS; i < NT; ++i) so[i - NS] = y0[i];
                 } else if (bdf.nst > 0 && (bdf.tn - tout) * bdf.h >= 0.0) {
-                    double yk[NS];
+                    double yk[NT];
                     bdf.get_dky(tout, yk);
 #pragma unroll
                     for (int i = 0; i < NS; ++i) yo[(size_t)k * NS + i] = yk[i];
+#pragma unroll
+                    for (int i = NS; i < NT; ++i) so[(size_t)k * (NT - NS) + i - NS] = yk[i];
                 } else {
                     break;
                 }
@@ -144,6 +165,7 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
     if (status != SB_SUCCESS) {
         // failed instances read as NaN, like the reference's Ops (as_pytensor.py:289-290)
         for (int j = 0; j < a.n_t * NS; ++j) yo[j] = qnan();
+        if (NBLK > 1) for (int j = 0; j < a.n_t * (NT - NS); ++j) so[j] = qnan();
     }
     a.status[inst] = status;
     if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
@@ -152,6 +174,13 @@ __device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long lo
         s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
         s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = bdf.nst + 1;
     }
+}
+
+__device__ __forceinline__ void forward_instance(const SbForwardArgs& a, long long inst, bool valid) {
+    forward_instance_t<1>(a, inst, valid);
+}
+__device__ __forceinline__ void forward_sens_instance(const SbForwardArgs& a, long long inst, bool valid) {
+    forward_instance_t<1 + ND>(a, inst, valid);
 }
 
 // ------------------------------------------------------------------------------------ tables
@@ -353,6 +382,14 @@ sb_forward(const __grid_constant__ SbForwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     sb::forward_instance(a, inst, inst < a.B);
 }
+
+#if SB_ND > 0
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_forward_sens(const __grid_constant__ SbForwardArgs a) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    sb::forward_sens_instance(a, inst, inst < a.B);
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(256)
 sb_tables(const SbTablesArgs a) {

@@ -143,7 +143,14 @@ class Solver(_ParamsMixin):
 
     Options of the reference that select other SUNDIALS modules are accepted for signature
     compatibility and rejected with ``NotImplementedError`` when they would change the
-    algorithm (ADAMS, non-dense linear solvers, constraints, forward sensitivities)."""
+    algorithm (ADAMS, non-dense linear solvers, constraints).
+
+    ``sens_mode`` = ``"simultaneous"`` or ``"staggered"`` turns on forward sensitivity analysis
+    (reference solver.py:360-392): y and dy/dp_k for the derivative parameters are integrated
+    together with the analytic sensitivity right-hand side and sensitivity error control, as the
+    reference configures CVODES.  The engine implements the simultaneous corrector; "staggered"
+    is accepted and runs the same kernel (the two differ in the order of the corrector
+    iterations, not in what is computed or in the error control)."""
 
     def __init__(self, problem: Problem, *, abstol=1e-10, reltol=1e-10,
                  sens_mode: Optional[str] = None, scaling_factors: Optional[np.ndarray] = None,
@@ -159,8 +166,18 @@ class Solver(_ParamsMixin):
         if linear_solver != 'dense':
             raise NotImplementedError(
                 'Only linear_solver="dense" (in-register LU with the analytic Jacobian) is implemented.')
-        if sens_mode is not None:
-            raise NotImplementedError('Forward sensitivities are not implemented yet; use AdjointSolver.')
+        if sens_mode == 'staggered1':
+            raise ValueError('staggered1 not implemented.')
+        if sens_mode not in (None, 'simultaneous', 'staggered'):
+            raise ValueError('sens_mode must be one of "simultaneous" and "staggered".')
+        if sens_mode is not None and problem.n_params == 0:
+            raise ValueError('Forward sensitivities need at least one derivative parameter.')
+        if scaling_factors is not None:
+            scaling_factors = np.asarray(scaling_factors, dtype=np.float64)
+            if scaling_factors.shape != (problem.n_params,):
+                raise ValueError('Invalid shape of scaling_factors.')
+            if not np.all(scaling_factors == 1.0):
+                raise NotImplementedError('scaling_factors other than 1 are not implemented.')
         if constraints is not None:
             raise NotImplementedError('Constraints are not implemented.')
         self._problem = problem
@@ -181,7 +198,7 @@ class Solver(_ParamsMixin):
         self._init_engine()
 
     def _init_engine(self) -> None:
-        self._compute_sens = False
+        self._compute_sens = self._sens_mode is not None
         self._engine = Engine(self._problem.generated, device=self._device,
                               block_threads=self._launch_cfg[0], min_blocks=self._launch_cfg[1])
         self._set_tolerances(self._abstol, self._reltol)
@@ -213,10 +230,16 @@ class Solver(_ParamsMixin):
         self._mxstep = int(mxstep)
 
     def make_output_buffers(self, tvals):
-        return np.zeros((len(tvals), self._problem.n_states))
+        n_states, n_params = self._problem.n_states, self._problem.n_params
+        y_vals = np.zeros((len(tvals), n_states))
+        if self._compute_sens:
+            return y_vals, np.zeros((len(tvals), n_params, n_states))
+        return y_vals
 
     # ------------------------------------------------------------------ batch-1, reference API
     def solve(self, t0, tvals, y0, y_out, *, sens0=None, sens_out=None, max_retries=5):
+        if self._compute_sens and (sens0 is None or sens_out is None):
+            raise ValueError('"sens_out" and "sens0" are required when computin sensitivities.')
         n_states = self._problem.n_states
         y0 = np.asarray(y0)
         if y0.dtype == self._problem.state_dtype and y0.dtype.fields is not None:
@@ -224,6 +247,15 @@ class Solver(_ParamsMixin):
         if y0.shape != (n_states,):
             raise ValueError(f"y0 should have shape {(n_states,)} but has shape {y0.shape}.")
         tvals = np.asarray(tvals, dtype=np.float64)
+        if self._compute_sens:
+            sens0 = np.ascontiguousarray(sens0, dtype=np.float64)
+            out, sens, status = self.solve_sens_batch(t0, tvals, y0[None, :], None, sens0,
+                                                      max_retries=max_retries)
+            if status[0] != 0:
+                _raise_forward(int(status[0]), tvals, out[0])
+            y_out[...] = out[0]
+            sens_out[...] = sens[0]
+            return
         out, status = self.solve_batch(t0, tvals, y0[None, :], None, max_retries=max_retries)
         if status[0] != 0:
             _raise_forward(int(status[0]), tvals, out[0])
@@ -244,6 +276,31 @@ class Solver(_ParamsMixin):
         self._engine.forward(float(t0), tvals, y0, params, y_out, status, stats,
                              store_history=False, stream=stream)
         return y_out, status
+
+
+def _solve_sens_batch(self, t0, tvals, y0, params, sens0, y_out=None, sens_out=None, *,
+                      status=None, stats=None, max_retries=5, stream=None):
+    """Batched solve with forward sensitivities: ``sens0`` is ``[n_deriv, n_states]`` (shared by
+    all instances) or ``[B, n_deriv, n_states]``.  Returns ``(y_out[B, n_t, n_s],
+    sens_out[B, n_t, n_deriv, n_s], status[B])``."""
+    if not self._compute_sens:
+        raise ValueError('The solver was created without sens_mode.')
+    y0 = self._flat_state(y0)
+    B = int(y0.shape[0])
+    tvals = np.asarray(tvals, dtype=np.float64)
+    params = self._batch_params(params, B)
+    if not _is_torch(sens0):
+        sens0 = np.ascontiguousarray(sens0, dtype=np.float64)
+    n_s, n_d = self._problem.n_states, self._problem.n_params
+    y_out, status = _alloc_like(y0, y_out, (B, len(tvals), n_s), status, B)
+    sens_out = _alloc_out(y0, sens_out, (B, len(tvals), n_d, n_s))
+    self._engine.set_max_num_steps(self._mxstep, max_retries)
+    self._engine.forward_sens(float(t0), tvals, y0, params, sens0, y_out, sens_out, status, stats,
+                              stream=stream)
+    return y_out, sens_out, status
+
+
+Solver.solve_sens_batch = _solve_sens_batch
 
 
 def _alloc_like(like, out, shape, status, B):

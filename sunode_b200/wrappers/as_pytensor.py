@@ -2,9 +2,8 @@
 ``sunode/wrappers/as_pytensor.py`` (``solve_ivp`` :20-137, ``EvalRhs`` :140-183,
 ``SolveODEAdjoint`` :266-308, ``SolveODEAdjointBackward`` :311-344).
 
-Same entry point, argument meaning and return tuple as the reference for
-``derivatives='adjoint'``; ``derivatives='forward'`` (CVODES forward sensitivities) is not
-implemented on this engine yet and raises ``NotImplementedError``.
+Same entry point, argument meaning and return tuples as the reference for
+``derivatives='adjoint'`` and ``derivatives='forward'`` (``SolveODE`` :186-263).
 
 PyTensor is optional at import time: the Ops' numeric bodies (``perform``) only need numpy and
 are exercised directly by the tests; building a graph (``solve_ivp``, ``Op.__call__``,
@@ -22,7 +21,7 @@ import numpy as np
 
 from .. import basic
 from ..dtypesubset import as_flattened
-from ..solver import AdjointSolver, SolverError
+from ..solver import AdjointSolver, Solver, SolverError
 from ..symode.problem import SympyProblem
 
 try:  # pragma: no cover - pytensor is not part of the build image
@@ -67,12 +66,13 @@ def solve_ivp(
     parameters.  Returns ``(solution_dict, flat_solution, problem, solver, y0_flat,
     params_subs_flat)``."""
     _need_pytensor()
-    if derivatives == 'forward':
-        raise NotImplementedError(
-            'derivatives="forward" (forward sensitivities) is not implemented; use "adjoint".')
-    if derivatives != 'adjoint':
-        raise ValueError('derivatives must be "adjoint"')
+    if derivatives not in ('adjoint', 'forward'):
+        raise ValueError('derivatives must be "adjoint" or "forward"')
     solver_kwargs = dict(solver_kwargs or {})
+    if derivatives == 'forward':
+        # sensitivities w.r.t. the initial values ride along as pseudo-parameters (:37-39)
+        params = dict(params)
+        params['__initial_values'] = y0
     dtype = basic.data_dtype
 
     def leaf(val):
@@ -118,6 +118,15 @@ def solve_ivp(
     t0 = pt.as_tensor_variable(t0, dtype='float64')
     tvals = pt.as_tensor_variable(tvals, dtype='float64')
 
+    if derivatives == 'forward':
+        if 'sens_mode' not in solver_kwargs:
+            raise ValueError('When `derivatives=True`, the `solver_kwargs` must contain one of '
+                             '`sens_mode={"simultaneous" | "staggered"}`.')
+        sol = make_solver(problem, **solver_kwargs) if make_solver else Solver(problem, **solver_kwargs)
+        wrapper = SolveODE(sol)
+        flat_solution, flat_sens = wrapper(y0_flat, params_subs_flat, params_remaining_flat, t0, tvals)
+        solution = problem.flat_solution_as_dict(flat_solution)
+        return (solution, flat_solution, problem, sol, y0_flat, params_subs_flat, flat_sens, wrapper)
     sol = make_solver(problem, **solver_kwargs) if make_solver else AdjointSolver(problem, **solver_kwargs)
     wrapper = SolveODEAdjoint(sol)
     flat_solution = wrapper(y0_flat, params_subs_flat, params_remaining_flat, t0, tvals)
@@ -164,6 +173,62 @@ class EvalRhs(_SolverOp):
         if not np.isfinite(out).all():
             raise ValueError('Bad ode rhs return code: 1')
         outputs[0][0] = out
+
+
+def initial_sensitivities(problem) -> np.ndarray:
+    """``sens0[n_deriv, n_states]``: zero, except that a derivative parameter living under
+    ``__initial_values`` is the initial value of the state with the same path, so its
+    sensitivity starts as the matching unit vector (reference :211-230)."""
+    subset = problem.params_subset
+    state_slices = problem.state_subset.flat_slices
+    sens0 = np.zeros((subset.n_subset, problem.n_states))
+    row = 0
+    for path in subset.subset_paths:
+        n_items = int(np.prod(subset.flat_shapes[path], dtype=int))
+        if path and path[0] == '__initial_values':
+            start = state_slices[tuple(path[1:])].start
+            for i in range(n_items):
+                sens0[row + i, start + i] = 1.0
+        row += n_items
+    return sens0
+
+
+class SolveODE(_SolverOp):
+    """Forward solve with forward sensitivities (reference :186-263): outputs the solution
+    ``[n_t, n_s]`` and ``d solution / d params`` ``[n_t, n_deriv, n_s]``."""
+    if HAVE_PYTENSOR:  # pragma: no cover
+        itypes = [pt.dvector, pt.dvector, pt.dvector, pt.dscalar, pt.dvector]
+        otypes = [pt.dmatrix, pt.dtensor3]
+
+    def __init__(self, solver):
+        super().__init__(solver)
+        self._sens0 = initial_sensitivities(solver._problem)
+
+    def perform(self, node, inputs, outputs):
+        y0, params, params_fixed, t0, tvals = inputs
+        y_out, sens_out = self._solver.make_output_buffers(tvals)
+        self._set_params(params, params_fixed)
+        try:
+            self._solver.solve(float(t0), tvals, np.asarray(y0, dtype=np.float64), y_out,
+                               sens0=self._sens0, sens_out=sens_out)
+        except SolverError:
+            y_out[...] = np.nan
+            sens_out[...] = np.nan
+        outputs[0][0] = y_out
+        outputs[1][0] = sens_out
+
+    def grad(self, inputs, g):  # pragma: no cover - needs pytensor
+        g, g_grad = g
+        _, params, params_fixed, t0, tvals = inputs
+        assert str(g_grad) == '<DisconnectedType>'
+        solution, sens = self(*inputs)
+        return [
+            pt.zeros_like(inputs[0]),
+            pt.sum(g[:, None, :] * sens, (0, -1)),
+            grad_not_implemented(self, 2, params_fixed),
+            grad_not_implemented(self, 3, t0),
+            (EvalRhs(self._solver)(params, params_fixed, solution, tvals) * g).sum(-1),
+        ]
 
 
 class SolveODEAdjoint(_SolverOp):

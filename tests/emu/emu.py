@@ -23,7 +23,8 @@ class ForwardArgs(ctypes.Structure):
     _fields_ = [('t0', ctypes.c_double), ('rtol', ctypes.c_double), ('tvals', _DP), ('y0', _DP),
                 ('params', _DP), ('atol', _DP), ('y_out', _DP), ('hist', _DP), ('hist_n', _IP),
                 ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong), ('n_t', ctypes.c_int),
-                ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int), ('pad_', ctypes.c_int)]
+                ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
+                ('sens0_shared', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP)]
 
 
 class TablesArgs(ctypes.Structure):
@@ -90,10 +91,27 @@ class Emulator:
         hist_n = np.zeros(B, dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,
-                        max_steps, 0)
+                        max_steps, 0, None, None)
         self.lib.emu_forward(ctypes.byref(a))
         return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
                     params=params, tvals=tvals)
+
+    def forward_sens(self, t0, tvals, y0, params, sens0, rtol, atol, max_steps=2500):
+        tvals = np.ascontiguousarray(tvals, dtype=np.float64)
+        y0, params, B = self._prep(y0, params)
+        n_t = len(tvals)
+        atol = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=np.float64), (self.ns,)))
+        sens0 = np.ascontiguousarray(sens0, dtype=np.float64)
+        shared = int(sens0.ndim == 2)
+        y_out = np.zeros((B, n_t, self.ns))
+        sens_out = np.zeros((B, n_t, self.nd, self.ns))
+        status = np.zeros(B, dtype=np.int32)
+        stats = np.zeros((B, STATS), dtype=np.int32)
+        a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
+                        None, None, _ip(status), _ip(stats), B, n_t, 0, max_steps, shared,
+                        _dp(sens0), _dp(sens_out))
+        self.lib.emu_forward_sens(ctypes.byref(a))
+        return dict(y=y_out, sens=sens_out, status=status, stats=stats)
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
                 rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000):

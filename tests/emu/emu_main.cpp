@@ -9,6 +9,10 @@ void emu_forward(const SbForwardArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
     for (long long i = 0; i < a->B; ++i) sb::forward_instance(*a, i, true);
 }
+void emu_forward_sens(const SbForwardArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i) sb::forward_sens_instance(*a, i, true);
+}
 void emu_tables(const SbTablesArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
     for (long long i = 0; i < a->B; ++i)
