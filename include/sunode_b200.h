@@ -104,6 +104,11 @@ int sb_solve_backward(sb_problem* p, int64_t B, double t_start, double t_end,
                       const double* tvals, int n_t, const double* params, const double* grads,
                       int grads_shared, double* grad_out, double* lamda_out, int32_t* status,
                       int32_t* stats, int mem, void* stream);
+/* Optional traces for the NEXT sb_solve_backward / sb_solve_adjoint call of this handle (cleared by
+ * it): lamda_all[B][n_t][n_states], quad_all[B][n_t][n_deriv] = lamda / quadrature right after the
+ * jump at each output time (`lamda_all_out`, `quad_all_out` of solver.py:723-724,778-781; same row
+ * convention).  The pointers live where that call's `mem` says.  Either may be NULL. */
+int sb_set_backward_trace(sb_problem* p, double* lamda_all, double* quad_all);
 
 /* One forward + one backward solve in a single call: the reference's unit of work
  * `solver.solve_forward(...); solver.solve_backward(tvals[-1], t0, tvals, grads, ...)`

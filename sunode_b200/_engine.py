@@ -217,10 +217,13 @@ class Engine:
             a_out.ptr, a_so.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream)))
 
     def backward(self, t_start: float, t_end: float, tvals, params, grads, grad_out, lamda_out,
-                 status, stats=None, *, stream: Optional[int] = None) -> None:
+                 status, stats=None, *, lamda_all=None, quad_all=None,
+                 stream: Optional[int] = None) -> None:
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)
         n_t = int(tvals.shape[0])
         B = int(lamda_out.shape[0])
+        a_la = _arg(lamda_all, (B, n_t, self.ns), 'lamda_all', writable=True, optional=True)
+        a_qa = _arg(quad_all, (B, n_t, self.nd), 'quad_all', writable=True, optional=True)
         shared = int(len(grads.shape) == 2)
         a_p = _arg(params, (B, self.np), 'params', optional=True)
         a_g = _arg(grads, (n_t, self.ns) if shared else (B, n_t, self.ns), 'grads')
@@ -229,7 +232,9 @@ class Engine:
         a_st = _arg(status, (B,), 'status', dtype=np.int32, writable=True)
         a_stats = _arg(stats, (B, _lib.SB_STATS_PER_INSTANCE), 'stats', dtype=np.int32,
                        writable=True, optional=True)
-        mem = _mem_kind([a_p, a_g, a_go, a_lo, a_st, a_stats])
+        mem = _mem_kind([a_p, a_g, a_go, a_lo, a_st, a_stats, a_la, a_qa])
+        if a_la.ptr is not None or a_qa.ptr is not None:
+            _lib.check(self._lib.sb_set_backward_trace(self._h, a_la.ptr, a_qa.ptr))
         _lib.check(self._lib.sb_solve_backward(
             self._h, B, float(t_start), float(t_end), tvals.ctypes.data, n_t, a_p.ptr, a_g.ptr,
             shared, a_go.ptr, a_lo.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream)))

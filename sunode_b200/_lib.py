@@ -57,6 +57,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         'sb_set_max_num_steps': (c_int, [_VP, c_int, c_int]),
         'sb_set_max_num_steps_b': (c_int, [_VP, c_int, c_int]),
         'sb_set_history_capacity': (c_int, [_VP, c_int]),
+        'sb_set_backward_trace': (c_int, [_VP, _VP, _VP]),
         'sb_solve_forward': (c_int, [_VP, c_i64, c_double, _VP, c_int, _VP, _VP, _VP, _VP, _VP,
                                      c_int, c_int, _VP]),
         'sb_solve_forward_sens': (c_int, [_VP, c_i64, c_double, _VP, c_int, _VP, _VP, _VP, c_int,
@@ -83,7 +84,7 @@ EXPORTS = (
     'sb_version', 'sb_last_error', 'sb_device_count', 'sb_compile', 'sb_free',
     'sb_problem_create', 'sb_problem_destroy', 'sb_set_tolerances', 'sb_set_tolerances_b',
     'sb_set_quad_tolerances_b', 'sb_set_max_num_steps', 'sb_set_max_num_steps_b',
-    'sb_set_history_capacity', 'sb_solve_forward', 'sb_solve_forward_sens', 'sb_solve_backward',
+    'sb_set_history_capacity', 'sb_set_backward_trace', 'sb_solve_forward', 'sb_solve_forward_sens', 'sb_solve_backward',
     'sb_solve_adjoint',
     'sb_eval', 'sb_synchronize', 'sb_last_kernel_ms', 'sb_launch_count', 'sb_kernel_info',
     'sb_host_alloc', 'sb_host_free',

@@ -61,6 +61,10 @@ typedef struct SbBackwardArgs {
     int hist_cap;
     int max_steps;            /* internal steps allowed per interval */
     int grads_shared;
+    /* optional traces (solver.py:778-781): lamda / quadrature right after the jump at each output
+     * time; row (n_t - k) % n_t for the k-th jump, as the reference's `lamda_all_out[-i]` indexing */
+    double* lamda_all;        /* [B][n_t][NS] or NULL */
+    double* quad_all;         /* [B][n_t][ND] or NULL */
 } SbBackwardArgs;
 
 typedef struct SbEvalArgs {

@@ -292,7 +292,6 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     double* lout = a.lamda_out + inst * NS;
     int status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
     const int np = a.hist_n[inst];
-    if (status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;   // no forward data
 
     Integrator bdf;
     BwdSys sys(a);
@@ -317,6 +316,9 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
         const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
         const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
         if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
+            // an interval to integrate over needs stored forward steps (none exist when every
+            // output time equals t0: then, as in the reference, only the jumps are applied)
+            if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
             const bool live = valid && status == SB_SUCCESS;
             if (live) {
                 bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
@@ -354,6 +356,16 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
             const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
 #pragma unroll
             for (int i = 0; i < NS; ++i) lam[i] -= g[i];
+            if (valid && (a.lamda_all || a.quad_all)) {
+                const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
+                const bool ok = status == SB_SUCCESS;
+                if (a.lamda_all)
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) a.lamda_all[row * NS + i] = ok ? lam[i] : qnan();
+                if (a.quad_all)
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) a.quad_all[row * ND + i] = ok ? quad[i] : qnan();
+            }
         }
     }
     if (!valid) return;

@@ -414,12 +414,14 @@ class AdjointSolver(_ParamsMixin):
 
     def solve_backward(self, t0, tend, tvals, grads, grad_out, lamda_out,
                        lamda_all_out=None, quad_all_out=None, max_retries=50):
-        if lamda_all_out is not None or quad_all_out is not None:
-            raise NotImplementedError('lamda_all_out / quad_all_out are not implemented.')
         tvals = np.asarray(tvals, dtype=np.float64)
-        grads = np.ascontiguousarray(grads, dtype=np.float64).reshape(1, len(tvals), self._problem.n_states)
+        n_s, n_d = self._problem.n_states, self._problem.n_params
+        grads = np.ascontiguousarray(grads, dtype=np.float64).reshape(1, len(tvals), n_s)
+        lam_all = np.empty((1, len(tvals), n_s)) if lamda_all_out is not None else None
+        quad_all = np.empty((1, len(tvals), n_d)) if quad_all_out is not None else None
         g, lam, status = self.solve_backward_batch(t0, tend, tvals, grads, None,
-                                                   max_retries=max_retries)
+                                                   max_retries=max_retries,
+                                                   lamda_all_out=lam_all, quad_all_out=quad_all)
         if status[0] != 0:
             code = int(status[0])
             if code == CV_TOO_MUCH_WORK:
@@ -428,6 +430,10 @@ class AdjointSolver(_ParamsMixin):
                               f"{ERRORS.get(code, 'UNKNOWN')} ({code})")
         grad_out[:] = g[0]
         lamda_out[:] = lam[0]
+        if lamda_all_out is not None:
+            lamda_all_out[...] = lam_all[0]
+        if quad_all_out is not None:
+            quad_all_out[...] = quad_all[0]
 
     # ------------------------------------------------------------------ batched
     def solve_forward_batch(self, t0, tvals, y0, params=None, y_out=None, *, status=None,
@@ -447,7 +453,7 @@ class AdjointSolver(_ParamsMixin):
 
     def solve_backward_batch(self, t0, tend, tvals, grads, params=None, grad_out=None,
                              lamda_out=None, *, status=None, stats=None, max_retries=50,
-                             stream=None):
+                             lamda_all_out=None, quad_all_out=None, stream=None):
         """Batched ``solve_backward`` on the stored forward pass.  ``t0`` is the LAST time and
         ``tend`` the initial time, as in the reference (solver.py:723-724).  ``grads`` is
         ``[B, n_t, n_states]`` or ``[n_t, n_states]`` (shared by all instances).  ``params=None``
@@ -466,7 +472,8 @@ class AdjointSolver(_ParamsMixin):
         lamda_out, status = _alloc_like(grads, lamda_out, (B, n_s), status, B)
         self._engine.set_max_num_steps_b(self._mxstep_b, max_retries)
         self._engine.backward(float(t0), float(tend), tvals, params, grads, grad_out, lamda_out,
-                              status, stats, stream=stream)
+                              status, stats, lamda_all=lamda_all_out, quad_all=quad_all_out,
+                              stream=stream)
         return grad_out, lamda_out, status
 
     def solve_adjoint_batch(self, t0, tvals, y0, params, grads, *, y_out=None, grad_out=None,

@@ -72,3 +72,26 @@ def test_tolerance_mxstep_and_capacity_limits(tmp_path):
     assert (r['status'] == -1).all()                                         # history overflow
     r = emu.forward(w.t0, w.tvals, y0, theta, 0.0, 0.0)                      # ewt undefined
     assert (r['status'] == -22).all()                                        # CV_ILL_INPUT
+
+
+def test_edge_cases_match_oracle(tmp_path):
+    """No parameters at all, no derivative parameters, a single output time equal to t0 (no
+    interval to integrate: only the jump is applied, solver.py:750-776), t0 among the outputs."""
+    from sunode_b200 import SympyProblem
+    prob = SympyProblem({}, {'x': ()}, lambda t, y, p: {'x': -y.x}, [])
+    emu = Emulator(prob, str(tmp_path / 'a'))
+    t = np.linspace(0.1, 1, 5)
+    r = emu.adjoint(0.0, t, np.ones((3, 1)), np.zeros((3, 0)), np.ones((5, 1)), 1e-8, 1e-8, hist_cap=128)
+    assert (r['status'] == 0).all() and r['grad'].shape == (3, 0)
+    np.testing.assert_allclose(-r['lamda'][:, 0], np.sum(np.exp(-t)), rtol=1e-6)
+
+    prob = SympyProblem({'k': ()}, {'x': ()}, lambda t, y, p: {'x': -p.k * y.x}, [])
+    emu = Emulator(prob, str(tmp_path / 'b'))
+    orc = Oracle(prob, rtol=1e-8, atol=1e-8)
+    for tv in (np.array([0.0]), np.array([0.0, 0.5]), np.array([0.25, 0.5])):
+        g = np.ones((len(tv), 1))
+        r = emu.adjoint(0.0, tv, np.ones((2, 1)), np.full((2, 1), 2.0), g, 1e-8, 1e-8, hist_cap=128)
+        yo, go, lo, so, _ = orc.solve_adjoint(0.0, tv, np.ones((2, 1)), np.full((2, 1), 2.0), g)
+        assert (r['status'] == 0).all() and (so == 0).all()
+        np.testing.assert_allclose(r['y'], yo, rtol=1e-9)
+        np.testing.assert_allclose(r['lamda'], lo, rtol=1e-9)

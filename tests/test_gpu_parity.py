@@ -184,3 +184,55 @@ def test_full_size_properties_lv():
     _, g3, lam3, _ = solver.solve_adjoint_batch(w.t0, w.tvals, y0[:4096], theta[:4096], 3.0 * g1)
     np.testing.assert_allclose(g3, 3.0 * g[:4096], rtol=2e-6, atol=1e-9 * np.abs(g).max())
     np.testing.assert_allclose(lam3, 3.0 * lam[:4096], rtol=2e-6, atol=1e-9 * np.abs(lam).max())
+
+
+def test_vector_atol_and_pickled_solver():
+    """CVodeSVtolerances (solver.py:404-407) and Solver pickling (solver.py:319-324: the
+    configuration travels, the engine handle is re-created)."""
+    import pickle
+    w = examples.workloads()['robertson_adj']
+    prob = w.make_problem()
+    B = 64
+    y0, theta = w.draws(B)
+    atol = np.array([1e-8, 1e-12, 1e-8])                 # the classic Robertson tolerances
+    solver = Solver(prob, abstol=atol, reltol=1e-8)
+    y, status = solver.solve_batch(w.t0, w.tvals, y0, theta)
+    yo, so, _ = _oracle(prob, rtol=1e-8, atol=atol).solve_forward(w.t0, w.tvals, y0, theta)
+    assert (status == 0).all() and (so == 0).all()
+    tol = 1e-8 * np.abs(yo) + atol
+    assert np.max(np.abs(y - yo) / tol) <= 1000.0
+    clone = pickle.loads(pickle.dumps(solver))
+    y2, status2 = clone.solve_batch(w.t0, w.tvals, y0, theta)
+    np.testing.assert_array_equal(y, y2)
+
+
+def test_edge_cases_and_backward_traces():
+    """Batch sizes that do not fill a warp, all output times equal to t0, and the optional
+    lamda_all_out / quad_all_out traces of solve_backward (solver.py:723-724, 778-781)."""
+    from sunode_b200 import SympyProblem
+    prob = SympyProblem({'k': ()}, {'x': ()}, lambda t, y, p: {'x': -p.k * y.x}, [('k',)])
+    solver = AdjointSolver(prob, abstol=1e-10, reltol=1e-10)
+    for B in (1, 33):
+        k = np.full((B, 1), 2.0)
+        y, g, lam, st = solver.solve_adjoint_batch(0.0, np.array([0.0]), np.ones((B, 1)), k,
+                                                  np.ones((1, 1)))
+        assert (st == 0).all()
+        np.testing.assert_array_equal(y[:, 0, 0], 1.0)
+        np.testing.assert_array_equal(lam[:, 0], -1.0)
+        np.testing.assert_array_equal(g[:, 0], 0.0)
+    # traces: x = exp(-k t); after the jump at t_i (walking backward) lamda = -sum_{j>=i} e^{-k(t_j-t_i)}
+    tv = np.array([0.5, 1.0, 1.5])
+    solver.set_params(np.array((2.0,), dtype=prob.params_dtype)[()])
+    y_out, grad_out, lamda_out = solver.make_output_buffers(tv)
+    solver.solve_forward(0.0, tv, np.ones(1), y_out)
+    lam_all, quad_all = np.zeros((3, 1)), np.zeros((3, 1))
+    solver.solve_backward(tv[-1], 0.0, tv, np.ones((3, 1)), grad_out, lamda_out,
+                          lamda_all_out=lam_all, quad_all_out=quad_all)
+    expect = {2: -1.0, 1: -(1 + np.exp(-1.0)), 0: -(1 + np.exp(-1.0) + np.exp(-2.0))}
+    # row convention of the reference: jump number i (0 = last time) lands in row (-i) % n_t
+    np.testing.assert_allclose(lam_all[0, 0], expect[2], rtol=1e-8)
+    np.testing.assert_allclose(lam_all[2, 0], expect[1], rtol=1e-8)
+    np.testing.assert_allclose(lam_all[1, 0], expect[0], rtol=1e-8)
+    np.testing.assert_allclose(-lamda_out[0], (np.exp(-1.0) + np.exp(-2.0) + np.exp(-3.0)), rtol=1e-8)
+    np.testing.assert_allclose(grad_out[0], np.sum(-tv * np.exp(-2.0 * tv)), rtol=1e-7)
+    assert quad_all[0, 0] == 0.0 and abs(quad_all[1, 0] - grad_out[0]) < abs(grad_out[0])
