@@ -250,9 +250,12 @@ class SympyProblem(Problem):
 
     # pickling: sympy objects pickle fine, the ctypes handle does not
     def __getstate__(self):
+        _ = self.generated          # the generated source travels; the user's callables need not
         state = dict(self.__dict__)
         state['_host'] = None
         state['_simplify'] = None
+        state['_rhs_sympy_func'] = None
+        state['_simplify_func'] = None
         # attribute trees of symbols: dynamically created dataclasses, only needed while the
         # user's rhs is being traced in __init__
         state['_sym_params'] = None
