@@ -95,7 +95,7 @@ class ClockSampler:
             except Exception as err:  # noqa: BLE001
                 self.err = repr(err)
                 break
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self._nv is not None:

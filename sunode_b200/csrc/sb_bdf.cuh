@@ -89,14 +89,13 @@ __device__ __forceinline__ void static_for(F&& f) {
 // well-scaled normal numbers, so it uses branch-free Newton sequences seeded by the SFU
 // approximations instead: results are within an ulp of the IEEE ones.  -DSB_EXACT_MATH restores
 // the IEEE operations (out of line, to keep the code small).
-#if defined(SB_EXACT_MATH) && !defined(SB_HOST_EMULATION)
-__device__ __noinline__ double sb_div(double a, double b) { return a / b; }
-__device__ __noinline__ double sb_sqrt(double a) { return sqrt(a); }
-#elif defined(SB_EXACT_MATH)
-__device__ __forceinline__ double sb_div(double a, double b) { return a / b; }
-__device__ __forceinline__ double sb_sqrt(double a) { return sqrt(a); }
-#else
+#ifdef SB_EXACT_MATH
+#define SB_EXACT_DIV 1
+#define SB_EXACT_SQRT 1
+#define SB_EXACT_ROOT 1
+#endif
 #ifdef SB_HOST_EMULATION
+#define SB_EXACT_FN __device__ __forceinline__
 // host stand-ins for the SFU seeds: the exact value with the low 32 mantissa bits cleared
 static inline double sb_seed_trunc(double v) {
     unsigned long long u; std::memcpy(&u, &v, 8); u &= 0xffffffff00000000ULL; std::memcpy(&v, &u, 8); return v;
@@ -104,6 +103,7 @@ static inline double sb_seed_trunc(double v) {
 static inline double sb_rcp_seed(double b) { return sb_seed_trunc(1.0 / b); }
 static inline double sb_rsqrt_seed(double x) { return sb_seed_trunc(1.0 / std::sqrt(x)); }
 #else
+#define SB_EXACT_FN __device__ __noinline__
 __device__ __forceinline__ double sb_rcp_seed(double b) {
     double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b)); return r;       // MUFU.RCP64H
 }
@@ -111,6 +111,9 @@ __device__ __forceinline__ double sb_rsqrt_seed(double x) {
     double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;     // MUFU.RSQ64H
 }
 #endif
+#ifdef SB_EXACT_DIV
+SB_EXACT_FN double sb_div(double a, double b) { return a / b; }
+#else
 __device__ __forceinline__ double sb_div(double a, double b) {
     double r = sb_rcp_seed(b);                                  // ~20 good bits
     double e = fma(-b, r, 1.0);
@@ -120,6 +123,10 @@ __device__ __forceinline__ double sb_div(double a, double b) {
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);                            // residual correction
 }
+#endif
+#ifdef SB_EXACT_SQRT
+SB_EXACT_FN double sb_sqrt(double a) { return sqrt(a); }
+#else
 __device__ __forceinline__ double sb_sqrt(double x) {
     double r = sb_rsqrt_seed(x);
     const double hx = 0.5 * x;
@@ -150,7 +157,7 @@ __device__ __forceinline__ double sb_ipow(double z, int k) {   // z^k, 0 <= k <=
 }
 SB_ROOT_FN double root_k(double x, int k) {
     if (k == 1) return x;
-#ifdef SB_EXACT_MATH
+#ifdef SB_EXACT_ROOT
     return pow(x, 1.0 / (double)k);
 #else
     if (!(x > 1e-30 && x < 1e30)) return pow(x, 1.0 / (double)k);   // 0, inf, nan, extreme: rare
