@@ -4,6 +4,7 @@
 #pragma once
 
 #define SB_STATS_STRIDE 8     /* ints per instance: nst nfe nje nsetups netf ncfn nni aux */
+#define SB_CARRY_INTS 10      /* status, table index, 7 counters, pad */
 
 /* history point: (t, order, y[NS])                         -> NS + 2 doubles
  * interpolation table entry for the interval (t_lo, t_hi):
@@ -65,6 +66,17 @@ typedef struct SbBackwardArgs {
      * time; row (n_t - k) % n_t for the k-th jump, as the reference's `lamda_all_out[-i]` indexing */
     double* lamda_all;        /* [B][n_t][NS] or NULL */
     double* quad_all;         /* [B][n_t][ND] or NULL */
+    /* segmented execution (n_seg > 1): the n_t + 1 intervals of a solve are cut into n_seg
+     * segments of seg_len intervals; a work unit = one segment of one group of 32 instances,
+     * handed out by a global counter to persistent warps (see sb_backward) */
+    int* queue;               /* [1] next unit, zeroed by the launcher */
+    int* seg_done;            /* [n_groups] segments completed per group, zeroed by the launcher */
+    double* carry_d;          /* [B][NS + max(ND,1)] lamda, quadrature between segments */
+    int* carry_i;             /* [B][SB_CARRY_INTS] status, table position, counters */
+    int n_seg;
+    int seg_len;
+    int n_groups;
+    int pad2_;
 } SbBackwardArgs;
 
 typedef struct SbEvalArgs {

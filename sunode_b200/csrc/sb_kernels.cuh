@@ -284,35 +284,52 @@ struct BwdSys {
 // Backward: the reference restarts the backward integrator at every output time
 // (CVodeReInitB + CVodeQuadReInitB, solver.py:756-757), so the interval loop stays and the lanes of
 // a warp -- which share tvals -- walk the intervals together; only the step loop inside an interval
-// is vote-driven.
-__device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst, bool valid) {
+// is vote-driven.  Because of those restarts NOTHING of the integrator survives an interval: only
+// lamda, the quadrature, the status and the table position do.  backward_unit therefore processes
+// any range [k_begin, k_end) of the n_t + 1 intervals, which lets the launcher cut a solve into
+// short work units (see sb_backward) -- the whole range is the plain one-warp-per-32-solves mode.
+#define SB_UNIT_TIMEOUT (-1005)
+__device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long inst, bool valid,
+                                              int k_begin, int k_end) {
     using Integrator = Bdf<NS, ND, BwdSys>;
     if (!valid) inst = 0;
-    double* gout = a.grad_out + inst * ND;
-    double* lout = a.lamda_out + inst * NS;
-    int status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
+    const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
 
     Integrator bdf;
     BwdSys sys(a);
     double lam[NS], quad[ND_];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) lam[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < ND_; ++i) quad[i] = 0.0;
+    int status;
     bdf.clear_stats();
+    sys.idx = np > 1 ? np - 1 : 1;
+    if (first) {
+        status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) lam[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < ND_; ++i) quad[i] = 0.0;
+    } else {
+        const double* cd = a.carry_d + (size_t)inst * (NS + ND_);
+        const int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) lam[i] = cd[i];
+#pragma unroll
+        for (int i = 0; i < ND_; ++i) quad[i] = cd[NS + i];
+        status = ci[0]; sys.idx = ci[1];
+        bdf.st.nst = ci[2]; bdf.st.nfe = ci[3]; bdf.st.nje = ci[4]; bdf.st.nsetups = ci[5];
+        bdf.st.netf = ci[6]; bdf.st.ncfn = ci[7]; bdf.st.nni = ci[8];
+    }
 
 #pragma unroll
     for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
     sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
     sys.np = np;
-    sys.idx = np > 1 ? np - 1 : 1;
     sys.t = 0.0;
     bdf.reinit(a.t_start, lam, quad);
 
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
     // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
-    for (int k = 0; k <= a.n_t; ++k) {
+    for (int k = k_begin; k < k_end; ++k) {
         const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
         const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
         if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
@@ -369,6 +386,20 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
         }
     }
     if (!valid) return;
+    if (!last) {
+        double* cd = a.carry_d + (size_t)inst * (NS + ND_);
+        int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) cd[i] = lam[i];
+#pragma unroll
+        for (int i = 0; i < ND_; ++i) cd[NS + i] = quad[i];
+        ci[0] = status; ci[1] = sys.idx;
+        ci[2] = bdf.st.nst; ci[3] = bdf.st.nfe; ci[4] = bdf.st.nje; ci[5] = bdf.st.nsetups;
+        ci[6] = bdf.st.netf; ci[7] = bdf.st.ncfn; ci[8] = bdf.st.nni;
+        return;
+    }
+    double* gout = a.grad_out + inst * ND;
+    double* lout = a.lamda_out + inst * NS;
     if (status != SB_SUCCESS) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) lam[i] = qnan();
@@ -387,8 +418,13 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
     }
 }
 
+__device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst, bool valid) {
+    backward_unit(a, inst, valid, 0, a.n_t + 1);
+}
+
 }  // namespace sb
 
+#ifndef SB_HOST_EMULATION   // the host emulation calls the *_instance functions directly
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,8 +449,47 @@ sb_tables(const SbTablesArgs a) {
 
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_backward(const __grid_constant__ SbBackwardArgs a) {
-    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    sb::backward_instance(a, inst, inst < a.B);
+    // Persistent warps pull work units (group of 32 instances x segment of intervals) from a global
+    // counter, in segment-major order.  A solve is ~1700 steps long and the batch is only ~1.7
+    // waves of resident warps, so with whole solves as units the second wave leaves a quarter of
+    // the machine idle for a full solve time; with short units the idle tail shrinks to one unit
+    // (n_seg = 1 is the whole-solve mode).  Unit (g, s) needs (g, s - 1): it was handed out
+    // n_groups units earlier, to a warp that is running or done (warps only wait on units handed
+    // out before their own, so there is no cycle); the wait is bounded all the same.
+    const int lane = threadIdx.x & 31;
+    const int total = a.n_seg * a.n_groups;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(a.queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total) break;
+        const int seg = u / a.n_groups, grp = u - seg * a.n_groups;
+        int timed_out = 0;
+        if (seg > 0) {
+            if (lane == 0) {
+                volatile int* done = a.seg_done;
+                int spins = 0;
+                while (done[grp] < seg) {
+                    __nanosleep(200);
+                    if (++spins > (1 << 23)) { timed_out = 1; break; }
+                }
+            }
+            timed_out = __shfl_sync(0xffffffffu, timed_out, 0);
+            __threadfence();
+        }
+        const long long inst = (long long)grp * 32 + lane;
+        const int k0 = seg * a.seg_len;
+        const int k1 = min(k0 + a.seg_len, a.n_t + 1);
+        if (timed_out) {
+            if (inst < a.B) a.carry_i[(size_t)inst * SB_CARRY_INTS] = SB_UNIT_TIMEOUT;
+            if (inst < a.B && k1 == a.n_t + 1) a.status[inst] = SB_UNIT_TIMEOUT;
+        } else {
+            sb::backward_unit(a, inst, inst < a.B, k0, k1);
+        }
+        __threadfence();
+        __syncwarp(0xffffffffu);
+        if (lane == 0) atomicExch(a.seg_done + grp, seg + 1);
+    }
 }
 
 extern "C" __global__ void __launch_bounds__(256)
@@ -450,3 +525,4 @@ sb_eval(const SbEvalArgs a) {
         for (int k = 0; k < ND; ++k) a.out[i * ND + k] = out[k];
     }
 }
+#endif  // SB_HOST_EMULATION

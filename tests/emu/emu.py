@@ -39,7 +39,10 @@ class BackwardArgs(ctypes.Structure):
                 ('tab', _DP), ('hist_n', _IP), ('fwd_status', _IP), ('grad_out', _DP),
                 ('lamda_out', _DP), ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong),
                 ('n_t', ctypes.c_int), ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
-                ('grads_shared', ctypes.c_int), ('lamda_all', _DP), ('quad_all', _DP)]
+                ('grads_shared', ctypes.c_int), ('lamda_all', _DP), ('quad_all', _DP),
+                ('queue', _IP), ('seg_done', _IP), ('carry_d', _DP), ('carry_i', _IP),
+                ('n_seg', ctypes.c_int), ('seg_len', ctypes.c_int), ('n_groups', ctypes.c_int),
+                ('pad2_', ctypes.c_int)]
 
 
 def _dp(a):
@@ -133,7 +136,8 @@ class Emulator:
         ba = BackwardArgs(rtol_b, atol_b, rtol_q, atol_q, float(fwd['tvals'][-1]), float(t0),
                           _dp(fwd['tvals']), _dp(fwd['params']), _dp(grads), _dp(tab),
                           _ip(fwd['hist_n']), _ip(fwd['status']), gptr, _dp(lam_out),
-                          _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared, None, None)
+                          _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared, None, None,
+                          None, None, None, None, 1, n_t + 1, 0, 0)
         self.lib.emu_backward(ctypes.byref(ba))
         return dict(y=fwd['y'], grad=grad_out, lamda=lam_out, status=status, stats=stats,
                     fwd=fwd, tab=tab)
