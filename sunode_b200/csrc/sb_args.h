@@ -32,6 +32,9 @@ typedef struct SbForwardArgs {
     /* forward sensitivities (sb_forward_sens only; NULL otherwise) */
     const double* sens0;      /* [B][ND][NS] or [ND][NS] */
     double* sens_out;         /* [B][n_t][ND][NS] */
+    /* when set (with hist): the interpolation table entry of every stored step is built by the
+     * forward kernel itself, right after the step, and the separate sb_tables launch is skipped */
+    double* tab;              /* [B][hist_cap][10 + 6*NS] or NULL */
 } SbForwardArgs;
 
 typedef struct SbTablesArgs {

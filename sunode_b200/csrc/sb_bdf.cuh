@@ -181,6 +181,15 @@ __device__ __forceinline__ bool all_finite(const double* v) {
     return s == 0.0;
 }
 
+// mean of the squared weighted components (wrms = sqrt of it)
+template <int N>
+__device__ __forceinline__ double wms(const double* v, const double* w) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double x = v[i] * w[i]; s = fma(x, x, s); }
+    return s * (1.0 / N);
+}
+
 template <int N>
 __device__ __forceinline__ double wrms(const double* v, const double* w) {
     double s = 0.0;
@@ -217,6 +226,7 @@ __device__ __forceinline__ bool lu_factor(double* a, int* piv) {
             }
         });
         const double mult = sb_div(1.0, a[k + N * k]);
+        a[k + N * k] = mult;        // the diagonal keeps the RECIPROCAL pivot: lu_solve multiplies
 #pragma unroll
         for (int i = k + 1; i < N; ++i) a[i + N * k] *= mult;
 #pragma unroll
@@ -248,7 +258,7 @@ __device__ __forceinline__ void lu_solve(const double* a, const int* piv, double
         for (int i = k + 1; i < N; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        b[k] = sb_div(b[k], a[k + N * k]);
+        b[k] *= a[k + N * k];
 #pragma unroll
         for (int i = 0; i < k; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
     }
@@ -706,7 +716,7 @@ struct Bdf {
             const double Cppinv = sb_div(1.0 - A6 + A5, A2);
             tq[3] = fabs(sb_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq[4] = sb_div(NLSCOEF, tq[2]);
+        tq[4] = tq[2] * (1.0 / NLSCOEF);   // 1 / (CVODES' tq[4] = nlscoef / tq[2]): used as a factor
         rl1 = sb_div(1.0, l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
@@ -785,7 +795,7 @@ struct Bdf {
                     for (int i = 0; i < N; ++i) { acor[i] += delta[i]; ycur[i] = zn[0][i] + acor[i]; }
                     const double del = norm(delta);
                     if (m > 0) crate = fmax(CRDOWN * crate, sb_div(del, delp));
-                    const double dcon = sb_div(del * fmin(1.0, crate), tq[4]);
+                    const double dcon = del * fmin(1.0, crate) * tq[4];
                     if (dcon <= 1.0) {
                         acnrm = (m == 0) ? del : norm(acor);
                         jcur = false;
@@ -1067,9 +1077,12 @@ struct Bdf {
     // Per-step bookkeeping CVode() does around cvStep for nst > 0.  Returns <0 on failure.
     __device__ __forceinline__ int pre_step_checks(const Sys& sys) {
         if (nst > 0 && !set_ewt(sys)) return SB_ILL_INPUT;
-        double nrm = norm(zn[0]);
-        if (QUAD) nrm = fmax(nrm, wrms<NQ_>(znQ[0], ewtQ));
-        if (SB_UROUND * nrm > 1.0) return SB_TOO_MUCH_ACC;
+        // tolsf = uround * ||y||_wrms > 1, tested on the squares (no square roots needed)
+        double nrm2 = wms<NM>(zn[0], ewt);
+#pragma unroll
+        for (int b = 1; b < NBLK; ++b) nrm2 = fmax(nrm2, wms<NM>(zn[0] + b * NM, ewt + b * NM));
+        if (QUAD) nrm2 = fmax(nrm2, wms<NQ_>(znQ[0], ewtQ));
+        if ((SB_UROUND * SB_UROUND) * nrm2 > 1.0) return SB_TOO_MUCH_ACC;
         return SB_SUCCESS;
     }
 

@@ -63,6 +63,53 @@ struct FwdSysT {
 };
 using FwdSys = FwdSysT<1>;
 
+// Interpolation table entry of the stored interval (idx - 1, idx): Newton divided differences
+// through the `order + 1` stored points ending at the interval's right end, scaled by the interval
+// length as CVODES does (CVApolynomialGetY); `order` is the BDF order of the step that produced
+// the right end point.  `hist` / `tab` are this instance's arrays.
+__device__ __forceinline__ void build_table_entry_at(const double* hist, double* tab, int idx) {
+    double* e = tab + (size_t)idx * TAB_STRIDE;
+    int order = (int)hist[(size_t)idx * HIST_STRIDE + 1];
+    if (order > idx) order = idx;
+    if (order < 1) order = 1;
+    double T[SB_LMAX], Y[SB_LMAX][NS];
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j) {
+        if (j <= order) {
+            const double* pnt = hist + (size_t)(idx - j) * HIST_STRIDE;
+            T[j] = pnt[0];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Y[j][k] = pnt[2 + k];
+        } else {
+            T[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Y[j][k] = 0.0;
+        }
+    }
+    const double delt = fabs(T[0] - T[1]);
+#pragma unroll
+    for (int i = 1; i < SB_LMAX; ++i) {
+#pragma unroll
+        for (int j = SB_LMAX - 1; j >= 1; --j) {
+            if (i <= order && j >= i && j <= order) {
+                const double factor = delt / (T[j] - T[j - i]);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) Y[j][k] = factor * (Y[j][k] - Y[j - 1][k]);
+            }
+        }
+    }
+    e[0] = T[1];
+    e[1] = T[0];
+    e[2] = (double)order;
+    e[3] = 1.0 / delt;
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j) e[4 + j] = T[j];
+#pragma unroll
+    for (int j = 0; j < SB_LMAX; ++j)
+#pragma unroll
+        for (int k = 0; k < NS; ++k) e[10 + NS * j + k] = Y[j][k];
+}
+
 __device__ __forceinline__ void store_point(double* hist, int idx, double t, int order, const double* y) {
     double* e = hist + (size_t)idx * HIST_STRIDE;
     e[0] = t;
@@ -104,6 +151,7 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
     double* yo = a.y_out + (size_t)inst * a.n_t * NS;
     double* so = (NBLK > 1) ? a.sens_out + (size_t)inst * a.n_t * (NT - NS) : nullptr;
     double* hist = a.hist ? a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE : nullptr;
+    double* tab = (a.hist && a.tab) ? a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE : nullptr;
     int status = SB_SUCCESS;
     int k = 0;          // next output time
     int nloc = 0;       // internal steps taken towards tvals[k] (CVode's nstloc, summed over retries)
@@ -154,7 +202,10 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
             const int r = bdf.attempt(sys, mask);
             if (r == SB_SUCCESS) {
                 nloc++;
-                if (hist) store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
+                if (hist) {
+                    store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
+                    if (tab) build_table_entry_at(hist, tab, bdf.nst);
+                }
             } else if (r != SB_TRY_AGAIN) {
                 status = r;
             }
@@ -184,53 +235,13 @@ __device__ __forceinline__ void forward_sens_instance(const SbForwardArgs& a, lo
 }
 
 // ------------------------------------------------------------------------------------ tables
-// One thread per (instance, interval).  Newton divided differences through the `order + 1` stored
-// points ending at the interval's right end, scaled by the interval length as CVODES does
-// (CVApolynomialGetY); `order` is the BDF order of the step that produced the right end point.
+// One thread per (instance, interval): the stand-alone version of the table construction (used when
+// the forward kernel did not build the tables itself).
 __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long long inst, int idx) {
     const int np = a.hist_n[inst];
     if (idx < 1 || idx >= np) return;
-    const double* hist = a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE;
-    double* e = a.tab + ((size_t)inst * a.hist_cap + idx) * TAB_STRIDE;
-    int order = (int)hist[(size_t)idx * HIST_STRIDE + 1];
-    if (order > idx) order = idx;
-    if (order < 1) order = 1;
-    double T[SB_LMAX], Y[SB_LMAX][NS];
-#pragma unroll
-    for (int j = 0; j < SB_LMAX; ++j) {
-        if (j <= order) {
-            const double* pnt = hist + (size_t)(idx - j) * HIST_STRIDE;
-            T[j] = pnt[0];
-#pragma unroll
-            for (int k = 0; k < NS; ++k) Y[j][k] = pnt[2 + k];
-        } else {
-            T[j] = 0.0;
-#pragma unroll
-            for (int k = 0; k < NS; ++k) Y[j][k] = 0.0;
-        }
-    }
-    const double delt = fabs(T[0] - T[1]);
-#pragma unroll
-    for (int i = 1; i < SB_LMAX; ++i) {
-#pragma unroll
-        for (int j = SB_LMAX - 1; j >= 1; --j) {
-            if (i <= order && j >= i && j <= order) {
-                const double factor = delt / (T[j] - T[j - i]);
-#pragma unroll
-                for (int k = 0; k < NS; ++k) Y[j][k] = factor * (Y[j][k] - Y[j - 1][k]);
-            }
-        }
-    }
-    e[0] = T[1];
-    e[1] = T[0];
-    e[2] = (double)order;
-    e[3] = 1.0 / delt;
-#pragma unroll
-    for (int j = 0; j < SB_LMAX; ++j) e[4 + j] = T[j];
-#pragma unroll
-    for (int j = 0; j < SB_LMAX; ++j)
-#pragma unroll
-        for (int k = 0; k < NS; ++k) e[10 + NS * j + k] = Y[j][k];
+    build_table_entry_at(a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE,
+                         a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE, idx);
 }
 
 // ------------------------------------------------------------------------------------ backward

@@ -24,7 +24,7 @@ class ForwardArgs(ctypes.Structure):
                 ('params', _DP), ('atol', _DP), ('y_out', _DP), ('hist', _DP), ('hist_n', _IP),
                 ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong), ('n_t', ctypes.c_int),
                 ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
-                ('sens0_shared', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP)]
+                ('sens0_shared', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP), ('tab', _DP)]
 
 
 class TablesArgs(ctypes.Structure):
@@ -82,7 +82,7 @@ class Emulator:
         params = np.ascontiguousarray(np.broadcast_to(params, (B, self.np))) if self.np else np.zeros((B, 1))
         return y0, params, B
 
-    def forward(self, t0, tvals, y0, params, rtol, atol, hist_cap=0, max_steps=2500):
+    def forward(self, t0, tvals, y0, params, rtol, atol, hist_cap=0, max_steps=2500, tab=None):
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)
         y0, params, B = self._prep(y0, params)
         n_t = len(tvals)
@@ -94,7 +94,7 @@ class Emulator:
         hist_n = np.zeros(B, dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,
-                        max_steps, 0, None, None)
+                        max_steps, 0, None, None, _dp(tab))
         self.lib.emu_forward(ctypes.byref(a))
         return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
                     params=params, tvals=tvals)
@@ -112,19 +112,25 @@ class Emulator:
         stats = np.zeros((B, STATS), dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         None, None, _ip(status), _ip(stats), B, n_t, 0, max_steps, shared,
-                        _dp(sens0), _dp(sens_out))
+                        _dp(sens0), _dp(sens_out), None)
         self.lib.emu_forward_sens(ctypes.byref(a))
         return dict(y=y_out, sens=sens_out, status=status, stats=stats)
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
                 rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000):
+        B0 = max(len(np.atleast_2d(y0)), len(np.atleast_2d(params)))
+        tab_fused = np.zeros((B0, hist_cap, 10 + 6 * self.ns))
         fwd = self.forward(t0, tvals, y0, params, rtol, atol, hist_cap=hist_cap,
-                           max_steps=2 ** 30)
+                           max_steps=2 ** 30, tab=tab_fused)
         B = len(fwd['status'])
         n_t = len(fwd['tvals'])
         tab = np.zeros((B, hist_cap, 10 + 6 * self.ns))
         ta = TablesArgs(_dp(fwd['hist']), _ip(fwd['hist_n']), _dp(tab), B, hist_cap, 0)
         self.lib.emu_tables(ctypes.byref(ta))
+        # the forward kernel's own tables (built step by step) must be the stand-alone ones
+        for b in range(B):
+            n = fwd['hist_n'][b]
+            assert np.array_equal(tab[b, 1:n], tab_fused[b, 1:n]), 'fused tables differ'
         grads = np.ascontiguousarray(grads, dtype=np.float64)
         shared = int(grads.ndim == 2)
         grad_out = np.zeros((B, max(self.nd, 1)))[:, :self.nd].copy() if self.nd else np.zeros((B, 0))
