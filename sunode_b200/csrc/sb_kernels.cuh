@@ -479,10 +479,13 @@ sb_backward(const __grid_constant__ SbBackwardArgs a) {
         if (seg > 0) {
             if (lane == 0) {
                 volatile int* done = a.seg_done;
-                int spins = 0;
+                unsigned long long t_begin = 0, t_now = 0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
                 while (done[grp] < seg) {
                     __nanosleep(200);
-                    if (++spins > (1 << 23)) { timed_out = 1; break; }
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                    // safety net only (a predecessor unit is always running or done): 60 s
+                    if (t_now - t_begin > 60000000000ULL) { timed_out = 1; break; }
                 }
             }
             timed_out = __shfl_sync(0xffffffffu, timed_out, 0);
