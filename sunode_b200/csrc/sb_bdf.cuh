@@ -198,42 +198,86 @@ __device__ __forceinline__ double wrms(const double* v, const double* w) {
     return sb_sqrt(s * (1.0 / N));
 }
 
-// ---- dense LU with partial pivoting, fully unrolled, rows swapped physically -----------------
-// a is column-major a[i + N*j].  The row permutation is recorded as N small ints.
+// ---- dense LU with partial pivoting ---------------------------------------------------------------
+// a is column-major a[i + N*j]; the row permutation is recorded as N small ints; the diagonal of
+// the factor holds the RECIPROCAL pivots.  Two implementations behind one interface:
+//  * N <= SB_LU_UNROLL_MAX: fully unrolled, rows swapped with selects so that every index is a
+//    literal and the matrix lives in registers;
+//  * larger N: plain loops with run-time indices; the matrix then lives in (L1-resident,
+//    lane-interleaved) local memory.  Measured on the 8-state SEIR problem the unrolled version is
+//    still the faster one (backward 219 ms vs 248 ms, forward 4.0 vs 10.7 ms), so the loop version
+//    only takes over beyond 8 states, where the unrolled select network (O(N^3)) stops compiling
+//    in reasonable time.
+#ifndef SB_LU_UNROLL_MAX
+#define SB_LU_UNROLL_MAX 8
+#endif
 template <int N>
 __device__ __forceinline__ bool lu_factor(double* a, int* piv) {
     bool ok = true;
+    if constexpr (N <= SB_LU_UNROLL_MAX) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        int l = k;
-        double best = fabs(a[k + N * k]);
+        for (int k = 0; k < N; ++k) {
+            int l = k;
+            double best = fabs(a[k + N * k]);
 #pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-            const double c = fabs(a[i + N * k]);
-            if (c > best) { best = c; l = i; }
-        }
-        piv[k] = l;
-        if (!(best > 0.0)) ok = false;
-        // swap rows k and l (l >= k) with selects so indices stay literal
-        static_for<0, N>([&](auto I_) {
-            constexpr int i = SB_IDX(I_);
-            const bool sw = (l == i) && (i > k);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double u = a[k + N * j], v = a[i + N * j];
-                a[k + N * j] = sw ? v : u;
-                a[i + N * j] = sw ? u : v;
+            for (int i = k + 1; i < N; ++i) {
+                const double c = fabs(a[i + N * k]);
+                if (c > best) { best = c; l = i; }
             }
-        });
-        const double mult = sb_div(1.0, a[k + N * k]);
-        a[k + N * k] = mult;        // the diagonal keeps the RECIPROCAL pivot: lu_solve multiplies
+            piv[k] = l;
+            if (!(best > 0.0)) ok = false;
+            // swap rows k and l (l >= k) with selects so indices stay literal
+            static_for<0, N>([&](auto I_) {
+                constexpr int i = SB_IDX(I_);
+                const bool sw = (l == i) && (i > k);
 #pragma unroll
-        for (int i = k + 1; i < N; ++i) a[i + N * k] *= mult;
+                for (int j = 0; j < N; ++j) {
+                    const double u = a[k + N * j], v = a[i + N * j];
+                    a[k + N * j] = sw ? v : u;
+                    a[i + N * j] = sw ? u : v;
+                }
+            });
+            const double mult = sb_div(1.0, a[k + N * k]);
+            a[k + N * k] = mult;
 #pragma unroll
-        for (int j = k + 1; j < N; ++j) {
-            const double akj = a[k + N * j];
+            for (int i = k + 1; i < N; ++i) a[i + N * k] *= mult;
 #pragma unroll
-            for (int i = k + 1; i < N; ++i) a[i + N * j] = fma(-akj, a[i + N * k], a[i + N * j]);
+            for (int j = k + 1; j < N; ++j) {
+                const double akj = a[k + N * j];
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) a[i + N * j] = fma(-akj, a[i + N * k], a[i + N * j]);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            int l = k;
+            double best = fabs(a[k + N * k]);
+#pragma unroll 1
+            for (int i = k + 1; i < N; ++i) {
+                const double c = fabs(a[i + N * k]);
+                if (c > best) { best = c; l = i; }
+            }
+            piv[k] = l;
+            if (!(best > 0.0)) ok = false;
+            if (l != k) {
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    const double u = a[k + N * j];
+                    a[k + N * j] = a[l + N * j];
+                    a[l + N * j] = u;
+                }
+            }
+            const double mult = sb_div(1.0, a[k + N * k]);
+            a[k + N * k] = mult;
+#pragma unroll 1
+            for (int i = k + 1; i < N; ++i) a[i + N * k] *= mult;
+#pragma unroll 1
+            for (int j = k + 1; j < N; ++j) {
+                const double akj = a[k + N * j];
+#pragma unroll 1
+                for (int i = k + 1; i < N; ++i) a[i + N * j] = fma(-akj, a[i + N * k], a[i + N * j]);
+            }
         }
     }
     return ok;
@@ -241,26 +285,55 @@ __device__ __forceinline__ bool lu_factor(double* a, int* piv) {
 
 template <int N>
 __device__ __forceinline__ void lu_solve(const double* a, const int* piv, double* b) {
+    if constexpr (N <= SB_LU_UNROLL_MAX) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const int l = piv[k];
-        static_for<0, N>([&](auto I_) {
-            constexpr int i = SB_IDX(I_);
-            const bool sw = (l == i) && (i > k);
-            const double u = b[k], v = b[i];
-            b[k] = sw ? v : u;
-            b[i] = sw ? u : v;
-        });
-    }
+        for (int k = 0; k < N; ++k) {
+            const int l = piv[k];
+            static_for<0, N>([&](auto I_) {
+                constexpr int i = SB_IDX(I_);
+                const bool sw = (l == i) && (i > k);
+                const double u = b[k], v = b[i];
+                b[k] = sw ? v : u;
+                b[i] = sw ? u : v;
+            });
+        }
 #pragma unroll
-    for (int k = 0; k < N - 1; ++k)
+        for (int k = 0; k < N - 1; ++k)
 #pragma unroll
-        for (int i = k + 1; i < N; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
+            for (int i = k + 1; i < N; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
 #pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-        b[k] *= a[k + N * k];
+        for (int k = N - 1; k >= 0; --k) {
+            b[k] *= a[k + N * k];
 #pragma unroll
-        for (int i = 0; i < k; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
+            for (int i = 0; i < k; ++i) b[i] = fma(-a[i + N * k], b[k], b[i]);
+        }
+    } else {
+        // the right-hand side is copied into a run-time indexed scratch vector and back
+        double x[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = b[i];
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const int l = piv[k];
+            const double u = x[k];
+            x[k] = x[l];
+            x[l] = u;
+        }
+#pragma unroll 1
+        for (int k = 0; k < N - 1; ++k) {
+            const double xk = x[k];
+#pragma unroll 1
+            for (int i = k + 1; i < N; ++i) x[i] = fma(-a[i + N * k], xk, x[i]);
+        }
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            const double xk = x[k] * a[k + N * k];
+            x[k] = xk;
+#pragma unroll 1
+            for (int i = 0; i < k; ++i) x[i] = fma(-a[i + N * k], xk, x[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) b[i] = x[i];
     }
 }
 
