@@ -95,3 +95,29 @@ def test_edge_cases_match_oracle(tmp_path):
         assert (r['status'] == 0).all() and (so == 0).all()
         np.testing.assert_allclose(r['y'], yo, rtol=1e-9)
         np.testing.assert_allclose(r['lamda'], lo, rtol=1e-9)
+
+
+def test_ten_state_chain_uses_loop_lu(tmp_path):
+    """A 10-state linear reaction chain: exercises the loop-based (run-time indexed) LU that
+    takes over beyond 8 states, against the oracle."""
+    from sunode_b200 import SympyProblem
+
+    def rhs(t, y, p):
+        x = y.x
+        out = []
+        for i in range(10):
+            inflow = p.k * x[i - 1] if i > 0 else 0
+            out.append(inflow - p.k * (1 + 0.1 * i) * x[i])
+        return {'x': out}
+
+    prob = SympyProblem({'k': ()}, {'x': 10}, rhs, [('k',)])
+    tv = np.linspace(0.2, 3.0, 8)
+    y0 = np.zeros((4, 10)); y0[:, 0] = 1.0
+    k = np.array([[0.5], [1.0], [2.0], [4.0]])
+    g = np.random.default_rng(0).standard_normal((8, 10))
+    r = Emulator(prob, str(tmp_path)).adjoint(0.0, tv, y0, k, g, 1e-8, 1e-8, hist_cap=512)
+    yo, go, lo, so, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(0.0, tv, y0, k, g)
+    assert (r['status'] == 0).all() and (so == 0).all()
+    assert np.max(np.abs(r['y'] - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
+    np.testing.assert_allclose(r['grad'], go, rtol=1e-7)
+    np.testing.assert_allclose(r['lamda'], lo, rtol=1e-7, atol=1e-12)
