@@ -140,10 +140,13 @@ __device__ __forceinline__ double sb_sqrt(double x) {
 }
 #endif
 
-// x^(1/k), k = 2..7, for the step-size controller (CVODES: SUNRpowerR(x, 1/k)).  One branch-free
-// sequence for every k: z ~ x^(-1/k) from the single-precision SFU log2/exp2, two division-free
-// Newton steps z <- z (1 + (1 - x z^k) / k), then x^(1/k) = x z^(k-1).  Good to a few ulp, like
-// pow(), at a quarter of its instructions; out of line because it has four call sites.
+// The step-size controller's ratio  eta = 1 / (x^(1/k) + ADDON),  k = 1..7  (CVODES:
+// 1 / (SUNRpowerR(x, 1/k) + ADDON) in cvCompleteStep / cvDoErrorTest / cvChooseEta).  One
+// branch-free sequence for every k: z0 ~ x^(-1/k) from the single-precision SFU log2/exp2
+// (relative error < 1e-6), the exact factor (1 + r)^(-1/k), r = x z0^k - 1, from its series to
+// second order (the r^3 term is below 1e-17), then eta = z / (1 + ADDON z).  Good to a few ulp,
+// like pow() followed by a division, at a fifth of the instructions; out of line because it has
+// four call sites.
 #ifdef SB_HOST_EMULATION
 static const double sb_rk_table[8] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7};
 #define SB_ROOT_FN inline
@@ -155,21 +158,22 @@ __device__ __forceinline__ double sb_ipow(double z, int k) {   // z^k, 0 <= k <=
     const double z2 = z * z, z4 = z2 * z2;
     return ((k & 1) ? z : 1.0) * ((k & 2) ? z2 : 1.0) * ((k & 4) ? z4 : 1.0);
 }
-SB_ROOT_FN double root_k(double x, int k) {
-    if (k == 1) return x;
+SB_ROOT_FN double eta_root(double x, int k) {
 #ifdef SB_EXACT_ROOT
-    return pow(x, 1.0 / (double)k);
+    return 1.0 / (((k == 1) ? x : pow(x, 1.0 / (double)k)) + ADDON);
 #else
-    if (!(x > 1e-30 && x < 1e30)) return pow(x, 1.0 / (double)k);   // 0, inf, nan, extreme: rare
+    if (!(x > 1e-30 && x < 1e30))                                    // 0, inf, nan, extreme: rare
+        return sb_div(1.0, ((k == 1) ? x : pow(x, 1.0 / (double)k)) + ADDON);
     const double rk = sb_rk_table[k];
 #ifdef SB_HOST_EMULATION
-    double z = (double)powf((float)x, -1.0f / (float)k);
+    const double z0 = (double)powf((float)x, -1.0f / (float)k);
 #else
-    double z = (double)exp2f(-__log2f((float)x) * (float)rk);
+    const double z0 = (double)exp2f(-__log2f((float)x) * (float)rk);
 #endif
-    z = fma(z * rk, fma(-x, sb_ipow(z, k), 1.0), z);
-    z = fma(z * rk, fma(-x, sb_ipow(z, k), 1.0), z);
-    return x * sb_ipow(z, k - 1);
+    const double r = fma(x, sb_ipow(z0, k), -1.0);
+    // (1 + r)^(-a) = 1 - a r + a (a + 1) / 2 r^2 - ...,  a = 1/k
+    const double z = z0 * fma(r * rk, fma(0.5 * (1.0 + rk), r, -1.0), 1.0);
+    return sb_div(z, fma(ADDON, z, 1.0));
 #endif
 }
 
@@ -944,7 +948,7 @@ struct Bdf {
             qprime = q; hprime = h; eta = 1.0;
             return;
         }
-        const double etaq = sb_div(1.0, root_k(BIAS2 * dsm, L) + ADDON);
+        const double etaq = eta_root(BIAS2 * dsm, L);
         if (qwait != 0) { eta = etaq; qprime = q; set_eta(); return; }
         qwait = 2;
         double etaqm1 = 0.0, etaqp1 = 0.0;
@@ -965,7 +969,7 @@ struct Bdf {
             double ddn = norm(zq);
             if (QUAD) ddn = fmax(ddn, wrms<NQ_>(zqQ, ewtQ));
             ddn *= tq[1];
-            etaqm1 = sb_div(1.0, root_k(BIAS1 * ddn, q) + ADDON);
+            etaqm1 = eta_root(BIAS1 * ddn, q);
         }
         if (q != SB_QMAX && saved_tq5 != 0.0) {
             const double r = sb_div(h, tau[2]);
@@ -984,7 +988,7 @@ struct Bdf {
                 dup = fmax(dup, wrms<NQ_>(tmpq, ewtQ));
             }
             dup *= tq[3];
-            etaqp1 = sb_div(1.0, root_k(BIAS3 * dup, L + 1) + ADDON);
+            etaqp1 = eta_root(BIAS3 * dup, L + 1);
         }
         const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
         if (etam < THRESH) { eta = 1.0; qprime = q; }
@@ -1011,7 +1015,7 @@ struct Bdf {
         if (nef_ == MXNEF) return SB_ERR_FAILURE;
         etamax = 1.0;
         if (nef_ <= MXNEF1) {
-            eta = sb_div(1.0, root_k(BIAS2 * dsm, L) + ADDON);
+            eta = eta_root(BIAS2 * dsm, L);
             eta = fmax(ETAMIN, eta);
             if (nef_ >= SMALL_NEF) eta = fmin(eta, ETAMXF);
             pend |= PEND_RESCALE;

@@ -22,6 +22,9 @@
 #ifndef SB_MIN_BLOCKS
 #define SB_MIN_BLOCKS 1
 #endif
+#ifndef SB_TAB_PREFETCH_MAX_NS
+#define SB_TAB_PREFETCH_MAX_NS 4
+#endif
 
 namespace sb {
 
@@ -265,26 +268,63 @@ struct BwdSys {
 
     __device__ __forceinline__ void set_time(double t_) {
         t = t_;
-        const double* e = tab + (size_t)idx * TAB_STRIDE;
-        // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
-        if (t < __ldg(e)) {
-            do { --idx; e -= TAB_STRIDE; } while (idx > 1 && t <= __ldg(e));
-            if (idx < 1) { idx = 1; e = tab + TAB_STRIDE; }
-        } else if (t > __ldg(e + 1)) {
-            while (idx < np - 1 && t > __ldg(e + 1)) { ++idx; e += TAB_STRIDE; }
-        }
-        const int order = (int)__ldg(e + 2);
-        const double inv_delt = __ldg(e + 3);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) yi[k] = __ldg(e + 10 + k);
-        double c = 1.0;
-        // rolled on purpose: the table lives in memory (dynamic indexing is free there) and the
-        // integrator is instruction-cache bound; this body is inlined at every set_time() site
+        if constexpr (NS <= SB_TAB_PREFETCH_MAX_NS) {
+            // Small systems: the whole table entry of the current interval is requested at once
+            // (independent loads, one memory latency), together with the interval bounds; only
+            // when t has left the interval (about one backward step in twenty) the position is
+            // moved and the entry fetched again.  Rows above `order` are stored as zeros, so the
+            // Newton form is evaluated over all SB_QMAX terms without a branch on the order.
+            const double* e = tab + (size_t)idx * TAB_STRIDE;
+            double lo, hi, inv_delt, T[SB_QMAX], Y[SB_LMAX][NS];
+            int order;
+            bool went_left = false;
 #pragma unroll 1
-        for (int i = 0; i < order; ++i) {
-            c *= (t - __ldg(e + 4 + i)) * inv_delt;
+            for (;;) {
+                lo = __ldg(e); hi = __ldg(e + 1);
+                order = (int)__ldg(e + 2);
+                inv_delt = __ldg(e + 3);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) yi[k] = fma(c, __ldg(e + 10 + NS * (i + 1) + k), yi[k]);
+                for (int i = 0; i < SB_QMAX; ++i) T[i] = __ldg(e + 4 + i);
+#pragma unroll
+                for (int j = 0; j < SB_LMAX; ++j)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) Y[j][k] = __ldg(e + 10 + NS * j + k);
+                // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
+                if ((t < lo || (went_left && t <= lo)) && idx > 1) { --idx; e -= TAB_STRIDE; went_left = true; }
+                else if (t > hi && idx < np - 1 && !went_left) { ++idx; e += TAB_STRIDE; }
+                else break;
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) yi[k] = Y[0][k];
+            double c = 1.0;
+#pragma unroll
+            for (int i = 0; i < SB_QMAX; ++i) {
+                c = (i < order) ? c * ((t - T[i]) * inv_delt) : 0.0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) yi[k] = fma(c, Y[i + 1][k], yi[k]);
+            }
+        } else {
+            const double* e = tab + (size_t)idx * TAB_STRIDE;
+            // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
+            if (t < __ldg(e)) {
+                do { --idx; e -= TAB_STRIDE; } while (idx > 1 && t <= __ldg(e));
+                if (idx < 1) { idx = 1; e = tab + TAB_STRIDE; }
+            } else if (t > __ldg(e + 1)) {
+                while (idx < np - 1 && t > __ldg(e + 1)) { ++idx; e += TAB_STRIDE; }
+            }
+            const int order = (int)__ldg(e + 2);
+            const double inv_delt = __ldg(e + 3);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) yi[k] = __ldg(e + 10 + k);
+            double c = 1.0;
+            // rolled on purpose: the table lives in memory (dynamic indexing is free there) and
+            // the integrator is instruction-cache bound; this body is inlined at every site
+#pragma unroll 1
+            for (int i = 0; i < order; ++i) {
+                c *= (t - __ldg(e + 4 + i)) * inv_delt;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) yi[k] = fma(c, __ldg(e + 10 + NS * (i + 1) + k), yi[k]);
+            }
         }
     }
     __device__ __forceinline__ void rhs(const double* lam, double* out) const { sb_adj_rhs(t, yi, lam, p, out); }
