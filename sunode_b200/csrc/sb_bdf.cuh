@@ -141,12 +141,13 @@ __device__ __forceinline__ double sb_sqrt(double x) {
 #endif
 
 // The step-size controller's ratio  eta = 1 / (x^(1/k) + ADDON),  k = 1..7  (CVODES:
-// 1 / (SUNRpowerR(x, 1/k) + ADDON) in cvCompleteStep / cvDoErrorTest / cvChooseEta).  One
-// branch-free sequence for every k: z0 ~ x^(-1/k) from the single-precision SFU log2/exp2
-// (relative error < 1e-6), the exact factor (1 + r)^(-1/k), r = x z0^k - 1, from its series to
-// second order (the r^3 term is below 1e-17), then eta = z / (1 + ADDON z).  Good to a few ulp,
-// like pow() followed by a division, at a fifth of the instructions; out of line because it has
-// four call sites.
+// 1 / (SUNRpowerR(x, 1/k) + ADDON) in cvCompleteStep / cvDoErrorTest / cvChooseEta), computed from
+// the SQUARE x2 = x^2 -- the integrator carries squared error norms so that no step needs a square
+// root.  One branch-free sequence for every k: z0 ~ x2^(-1/(2k)) from the single-precision SFU
+// log2/exp2 (relative error < 1e-6), the exact factor (1 + r)^(-1/(2k)), r = x2 z0^(2k) - 1, from
+// its series to second order (the r^3 term is below 1e-16), then eta = z / (1 + ADDON z).  Good to
+// a few ulp, like sqrt() + pow() + a division, at a sixth of the instructions; out of line because
+// it has four call sites.
 #ifdef SB_HOST_EMULATION
 static const double sb_rk_table[8] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7};
 #define SB_ROOT_FN inline
@@ -158,21 +159,21 @@ __device__ __forceinline__ double sb_ipow(double z, int k) {   // z^k, 0 <= k <=
     const double z2 = z * z, z4 = z2 * z2;
     return ((k & 1) ? z : 1.0) * ((k & 2) ? z2 : 1.0) * ((k & 4) ? z4 : 1.0);
 }
-SB_ROOT_FN double eta_root(double x, int k) {
+SB_ROOT_FN double eta_root2(double x2, int k) {
 #ifdef SB_EXACT_ROOT
-    return 1.0 / (((k == 1) ? x : pow(x, 1.0 / (double)k)) + ADDON);
+    return 1.0 / (pow(x2, 0.5 / (double)k) + ADDON);
 #else
-    if (!(x > 1e-30 && x < 1e30))                                    // 0, inf, nan, extreme: rare
-        return sb_div(1.0, ((k == 1) ? x : pow(x, 1.0 / (double)k)) + ADDON);
-    const double rk = sb_rk_table[k];
+    if (!(x2 > 1e-36 && x2 < 1e36))                                  // 0, inf, nan, extreme: rare
+        return sb_div(1.0, pow(x2, 0.5 / (double)k) + ADDON);
+    const double a = 0.5 * sb_rk_table[k];
 #ifdef SB_HOST_EMULATION
-    const double z0 = (double)powf((float)x, -1.0f / (float)k);
+    const double z0 = (double)powf((float)x2, -0.5f / (float)k);
 #else
-    const double z0 = (double)exp2f(-__log2f((float)x) * (float)rk);
+    const double z0 = (double)exp2f(-__log2f((float)x2) * (float)a);
 #endif
-    const double r = fma(x, sb_ipow(z0, k), -1.0);
-    // (1 + r)^(-a) = 1 - a r + a (a + 1) / 2 r^2 - ...,  a = 1/k
-    const double z = z0 * fma(r * rk, fma(0.5 * (1.0 + rk), r, -1.0), 1.0);
+    const double r = fma(x2, sb_ipow(z0 * z0, k), -1.0);
+    // (1 + r)^(-a) = 1 - a r + a (a + 1) / 2 r^2 - ...,  a = 1/(2k)
+    const double z = z0 * fma(r * a, fma(0.5 * (1.0 + a), r, -1.0), 1.0);
     return sb_div(z, fma(ADDON, z, 1.0));
 #endif
 }
@@ -364,6 +365,16 @@ struct Bdf {
         for (int b = 1; b < NBLK; ++b) r = fmax(r, wrms<NM>(v + b * NM, ewt + b * NM));
         return r;
     }
+    // Its square.  Every test a step makes on a norm (Newton convergence, error test, tolsf) and
+    // the step-size ratios are monotone in the norm, so the step loop works on squares throughout
+    // and takes no square roots (names ending in 2: del2, delp2, crate2, acnrm2, dsm2; tq[1..4]
+    // hold the squares of CVODES' test quantities).  Only cvHin still needs norms proper.
+    __device__ __forceinline__ double norm2(const double* v) const {
+        double r = wms<NM>(v, ewt);
+#pragma unroll
+        for (int b = 1; b < NBLK; ++b) r = fmax(r, wms<NM>(v + b * NM, ewt + b * NM));
+        return r;
+    }
 
     // Nordsieck arrays
     double zn[SB_LMAX][N], zsave[N], acor[N], ewt[N];
@@ -372,7 +383,7 @@ struct Bdf {
     // step / order control
     double tau[SB_LMAX + 1], l[SB_LMAX], tq[6];
     double h, hprime, hscale, eta, etamax, tn, hu;
-    double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+    double rl1, gamma, gammap, gamrat, crate2, delp2, acnrm2, saved_tq5;
     int q, qprime, qwait, L, qu;
     bool jcur;
     // linear solver
@@ -411,7 +422,7 @@ struct Bdf {
         for (int j = 0; j <= SB_LMAX; ++j) tau[j] = 0.0;
         q = 1; L = 2; qwait = 2; qprime = 1; etamax = ETAMX1; qu = 0; hu = 0.0;
         nst = 0; nstlp = 0; nstlj = 0;
-        saved_tq5 = 0.0; jcur = false; crate = 1.0; delp = 0.0; acnrm = 0.0;
+        saved_tq5 = 0.0; jcur = false; crate2 = 1.0; delp2 = 0.0; acnrm2 = 0.0;
         h = hprime = hscale = 0.0; eta = 1.0; gamma = gammap = gamrat = 1.0; rl1 = 1.0;
         in_step = false; step_t0 = t0; ncf = nef = nefQ = 0; nflag = FIRST_CALL; pend = 0;
     }
@@ -776,7 +787,8 @@ struct Bdf {
         });
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        tq[2] = fabs(sb_div(A1, alpha0 * A2));
+        const double tq2 = sb_div(A1, alpha0 * A2);
+        tq[2] = tq2 * tq2;
         tq[5] = fabs(sb_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
@@ -784,16 +796,17 @@ struct Bdf {
                 const double A3 = alpha0 + sb_rk_table[q];
                 const double A4 = alpha0_hat + xi_inv;
                 const double Cpinv = sb_div(1.0 - A4 + A3, A3);
-                tq[1] = fabs(C * Cpinv);
+                tq[1] = (C * Cpinv) * (C * Cpinv);
             } else tq[1] = 1.0;
             hsum += tau_q;
             xi_inv = sb_div(h, hsum);
             const double A5 = alpha0 - sb_rk_table[q + 1];
             const double A6 = alpha0_hat - xi_inv;
             const double Cppinv = sb_div(1.0 - A6 + A5, A2);
-            tq[3] = fabs(sb_div(Cppinv, xi_inv * (q + 2) * A5));
+            const double tq3 = sb_div(Cppinv, xi_inv * (q + 2) * A5);
+            tq[3] = tq3 * tq3;
         }
-        tq[4] = tq[2] * (1.0 / NLSCOEF);   // 1 / (CVODES' tq[4] = nlscoef / tq[2]): used as a factor
+        tq[4] = tq[2] * (1.0 / (NLSCOEF * NLSCOEF));   // (tq[2] / nlscoef)^2 = 1 / CVODES' tq[4]^2, a factor
         rl1 = sb_div(1.0, l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
@@ -848,7 +861,7 @@ struct Bdf {
                 const int r = lsetup(sys, convfail, ycur);
                 st.nsetups++;
                 callSetup = false;
-                gamrat = 1.0; gammap = gamma; crate = 1.0; nstlp = nst;
+                gamrat = 1.0; gammap = gamma; crate2 = 1.0; nstlp = nst;
                 if (r != 0) { done = true; live = false; }
             }
             sb_sync(mask);
@@ -870,19 +883,19 @@ struct Bdf {
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) { acor[i] += delta[i]; ycur[i] = zn[0][i] + acor[i]; }
-                    const double del = norm(delta);
-                    if (m > 0) crate = fmax(CRDOWN * crate, sb_div(del, delp));
-                    const double dcon = del * fmin(1.0, crate) * tq[4];
-                    if (dcon <= 1.0) {
-                        acnrm = (m == 0) ? del : norm(acor);
+                    const double del2 = norm2(delta);
+                    if (m > 0) crate2 = fmax((CRDOWN * CRDOWN) * crate2, sb_div(del2, delp2));
+                    const double dcon2 = del2 * fmin(1.0, crate2) * tq[4];
+                    if (dcon2 <= 1.0) {
+                        acnrm2 = (m == 0) ? del2 : norm2(acor);
                         jcur = false;
                         retval = 0; done = true; run = false;
-                    } else if (!(dcon > 1.0)) {                       // NaN
+                    } else if (!(dcon2 > 1.0)) {                      // NaN
                         run = false;
-                    } else if (m >= 1 && del > RDIV * delp) {         // diverging
+                    } else if (m >= 1 && del2 > (RDIV * RDIV) * delp2) {   // diverging
                         run = false;
                     } else {
-                        delp = del;
+                        delp2 = del2;
                         if (m + 1 >= NLS_MAXCOR) {
                             run = false;
                         } else {
@@ -942,13 +955,13 @@ struct Bdf {
         else { eta = fmin(eta, etamax); hprime = h * eta; }
     }
 
-    __device__ __forceinline__ void prepare_next_step(double dsm) {
+    __device__ __forceinline__ void prepare_next_step(double dsm2) {
         if (etamax == 1.0) {
             qwait = max(qwait, 2);
             qprime = q; hprime = h; eta = 1.0;
             return;
         }
-        const double etaq = eta_root(BIAS2 * dsm, L);
+        const double etaq = eta_root2((BIAS2 * BIAS2) * dsm2, L);
         if (qwait != 0) { eta = etaq; qprime = q; set_eta(); return; }
         qwait = 2;
         double etaqm1 = 0.0, etaqp1 = 0.0;
@@ -966,10 +979,10 @@ struct Bdf {
 #pragma unroll
                 for (int i = 0; i < NQ_; ++i) zqQ[i] = is_q ? znQ[j][i] : zqQ[i];
             });
-            double ddn = norm(zq);
-            if (QUAD) ddn = fmax(ddn, wrms<NQ_>(zqQ, ewtQ));
-            ddn *= tq[1];
-            etaqm1 = eta_root(BIAS1 * ddn, q);
+            double ddn2 = norm2(zq);
+            if (QUAD) ddn2 = fmax(ddn2, wms<NQ_>(zqQ, ewtQ));
+            ddn2 *= tq[1];
+            etaqm1 = eta_root2((BIAS1 * BIAS1) * ddn2, q);
         }
         if (q != SB_QMAX && saved_tq5 != 0.0) {
             const double r = sb_div(h, tau[2]);
@@ -980,15 +993,15 @@ struct Bdf {
             double tmp[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) tmp[i] = fma(-cquot, zsave[i], acor[i]);
-            double dup = norm(tmp);
+            double dup2 = norm2(tmp);
             if (QUAD) {
                 double tmpq[NQ_];
 #pragma unroll
                 for (int i = 0; i < NQ_; ++i) tmpq[i] = fma(-cquot, zsaveQ[i], acorQ[i]);
-                dup = fmax(dup, wrms<NQ_>(tmpq, ewtQ));
+                dup2 = fmax(dup2, wms<NQ_>(tmpq, ewtQ));
             }
-            dup *= tq[3];
-            etaqp1 = eta_root(BIAS3 * dup, L + 1);
+            dup2 *= tq[3];
+            etaqp1 = eta_root2((BIAS3 * BIAS3) * dup2, L + 1);
         }
         const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
         if (etam < THRESH) { eta = 1.0; qprime = q; }
@@ -1009,13 +1022,13 @@ struct Bdf {
     // Tail of a failed error test (cvDoErrorTest after the `dsm > 1` branch): decides how the
     // step is retried; the history manipulation itself is queued in `pend`.
     // returns 0 = try again, <0 = fatal
-    __device__ __forceinline__ int error_test_failed(double dsm, int nef_) {
+    __device__ __forceinline__ int error_test_failed(double dsm2, int nef_) {
         st.netf++;
         pend = PEND_RESTORE;
         if (nef_ == MXNEF) return SB_ERR_FAILURE;
         etamax = 1.0;
         if (nef_ <= MXNEF1) {
-            eta = eta_root(BIAS2 * dsm, L);
+            eta = eta_root2((BIAS2 * BIAS2) * dsm2, L);
             eta = fmax(ETAMIN, eta);
             if (nef_ >= SMALL_NEF) eta = fmin(eta, ETAMXF);
             pend |= PEND_RESCALE;
@@ -1056,7 +1069,7 @@ struct Bdf {
             set_coeffs();
         }
         const int nr = nls(sys, nflag, mask, go);
-        double dsm = 0.0;
+        double dsm2 = 0.0;
         if (go) {
             if (nr != 0) {
                 // cvHandleNFlag
@@ -1071,11 +1084,11 @@ struct Bdf {
                     result = SB_TRY_AGAIN;
                 }
             } else {
-                dsm = acnrm * tq[2];
-                if (!(dsm <= 1.0)) {
+                dsm2 = acnrm2 * tq[2];
+                if (!(dsm2 <= 1.0)) {
                     nef++;
                     nflag = PREV_ERR_FAIL;
-                    const int r = error_test_failed(dsm, nef);
+                    const int r = error_test_failed(dsm2, nef);
                     go = false;
                     if (r < 0) { in_step = false; result = r; }
                     else result = SB_TRY_AGAIN;
@@ -1102,16 +1115,16 @@ struct Bdf {
                 } else {
 #pragma unroll
                     for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
-                    const double dsmQ = wrms<NQ_>(acorQ, ewtQ) * tq[2];
-                    if (!(dsmQ <= 1.0)) {
+                    const double dsmQ2 = wms<NQ_>(acorQ, ewtQ) * tq[2];
+                    if (!(dsmQ2 <= 1.0)) {
                         nefQ++;
                         nflag = PREV_ERR_FAIL;
-                        const int r = error_test_failed(dsmQ, nefQ);
+                        const int r = error_test_failed(dsmQ2, nefQ);
                         go = false;
                         if (r < 0) { in_step = false; result = r; }
                         else result = SB_TRY_AGAIN;
                     } else {
-                        dsm = fmax(dsm, dsmQ);
+                        dsm2 = fmax(dsm2, dsmQ2);
                     }
                 }
             }
@@ -1119,7 +1132,7 @@ struct Bdf {
         sb_sync(mask);
         if (go) {
             complete_step();
-            prepare_next_step(dsm);
+            prepare_next_step(dsm2);
             etamax = (nst <= SMALL_NST) ? ETAMX2 : ETAMX3;
             // (CVODES rescales acor by tq[2] here to expose the local error estimate; nothing on
             // this path reads it before the next step overwrites it, so it is not materialised.)
