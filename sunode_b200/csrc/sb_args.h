@@ -29,12 +29,17 @@ typedef struct SbForwardArgs {
     int hist_cap;
     int max_steps;            /* internal steps allowed per output time */
     int sens0_shared;         /* sens0 is [ND][NS] for all instances instead of [B][ND][NS] */
+    int lanes;                /* lanes of a warp that carry an instance (32) */
+    int pad_;
     /* forward sensitivities (sb_forward_sens only; NULL otherwise) */
     const double* sens0;      /* [B][ND][NS] or [ND][NS] */
     double* sens_out;         /* [B][n_t][ND][NS] */
     /* when set (with hist): the interpolation table entry of every stored step is built by the
      * forward kernel itself, right after the step, and the separate sb_tables launch is skipped */
     double* tab;              /* [B][hist_cap][10 + 6*NS] or NULL */
+    /* when set: the accepted steps of all successful instances are added up here; the backward
+     * kernels choose their interval schedule from it (see SbBackwardArgs.steps_total) */
+    unsigned long long* steps_total;
 } SbForwardArgs;
 
 typedef struct SbTablesArgs {
@@ -78,8 +83,18 @@ typedef struct SbBackwardArgs {
     int* carry_i;             /* [B][SB_CARRY_INTS] status, table position, counters */
     int n_seg;
     int seg_len;
-    int n_groups;
+    int n_groups;             /* ceil(B / lanes) */
+    int lanes;                /* lanes of a warp that carry an instance (32; fewer only as an
+                               * experiment, see lanes_per_warp in sb_api.cpp) */
+    int flat;                 /* sb_backward_flat: when a lane starts its next interval: 0 with the
+                               * other lanes of the warp, 1 at once, -1 the warp decides */
     int pad2_;
+    /* Two builds of the backward kernel are launched back to back, sb_backward (lanes of a warp walk
+     * the intervals together) and sb_backward_flat (every lane on its own); the one whose schedule
+     * does not suit the stored forward solve returns at once: flat runs iff
+     * *steps_total > flat_steps (forward steps of the whole batch; NULL: the plain kernel runs). */
+    const unsigned long long* steps_total;
+    unsigned long long flat_steps;
 } SbBackwardArgs;
 
 typedef struct SbEvalArgs {

@@ -25,6 +25,9 @@
 #ifndef SB_TAB_PREFETCH_MAX_NS
 #define SB_TAB_PREFETCH_MAX_NS 4
 #endif
+#ifndef SB_FLAT_IDLE
+#define SB_FLAT_IDLE 16     /* mean passes a lane may wait per interval before the warp goes flat */
+#endif
 
 namespace sb {
 
@@ -214,6 +217,15 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
             }
         }
     }
+    if (a.steps_total) {
+#ifndef SB_HOST_EMULATION
+        unsigned n = (valid && status == SB_SUCCESS) ? (unsigned)bdf.nst : 0u;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(a.steps_total, (unsigned long long)n);
+#else
+        if (status == SB_SUCCESS) *a.steps_total += (unsigned long long)bdf.nst;
+#endif
+    }
     if (!valid) return;
 
     if (status != SB_SUCCESS) {
@@ -333,13 +345,26 @@ struct BwdSys {
 };
 
 // Backward: the reference restarts the backward integrator at every output time
-// (CVodeReInitB + CVodeQuadReInitB, solver.py:756-757), so the interval loop stays and the lanes of
-// a warp -- which share tvals -- walk the intervals together; only the step loop inside an interval
-// is vote-driven.  Because of those restarts NOTHING of the integrator survives an interval: only
-// lamda, the quadrature, the status and the table position do.  backward_unit therefore processes
-// any range [k_begin, k_end) of the n_t + 1 intervals, which lets the launcher cut a solve into
-// short work units (see sb_backward) -- the whole range is the plain one-warp-per-32-solves mode.
+// (CVodeReInitB + CVodeQuadReInitB, solver.py:756-757).  Because of those restarts NOTHING of the
+// integrator survives an interval: only lamda, the quadrature, the status and the table position
+// do.  backward_unit therefore processes any range [k_begin, k_end) of the n_t + 1 intervals, which
+// lets the launcher cut a solve into short work units (see sb_backward) -- the whole range is the
+// plain one-warp-per-32-solves mode.
+//
+// Every lane walks its intervals with its own counter; what differs between the two modes is when
+// a lane that has reached the end of its interval starts the next one:
+//  * barrier mode: when no lane of the warp is stepping any more, so that the restart (order-1
+//    re-initialisation + cvHin, a long divergent block) runs once per interval for all lanes.  Best
+//    when the lanes need about the same number of steps per interval (Lotka-Volterra, SEIR: the
+//    wait costs 13-19 % of the lane-passes, restarting lane by lane would cost more);
+//  * flat mode: at once.  For stiff problems the steps per interval differ wildly between draws
+//    (Robertson: the wait idles 51 % of the lane-passes, restarts are rare against ~400 passes per
+//    interval); tools/lane_efficiency.py has the numbers.
+// a.flat selects: 0 barrier, 1 flat, -1 the warp decides -- it starts in barrier mode and goes flat
+// for good once the lanes of an interval waited more than SB_FLAT_IDLE passes each on average.
+// The per-lane sequence of operations is the same in every mode, results do not depend on it.
 #define SB_UNIT_TIMEOUT (-1005)
+template <bool FLAT>
 __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long inst, bool valid,
                                               int k_begin, int k_end) {
     using Integrator = Bdf<NS, ND, BwdSys>;
@@ -379,60 +404,137 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
     bdf.reinit(a.t_start, lam, quad);
 
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
-    // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
-    for (int k = k_begin; k < k_end; ++k) {
-        const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
-        const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
-        if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
-            // an interval to integrate over needs stored forward steps (none exist when every
-            // output time equals t0: then, as in the reference, only the jumps are applied)
-            if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
-            const bool live = valid && status == SB_SUCCESS;
-            if (live) {
-                bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
-                status = bdf.first_call(sys, t_lower);
-            }
-            int nloc = 0;
-            bool reached = false;
-            for (;;) {
-                bool work = valid && status == SB_SUCCESS && !reached;
-                if (work && !bdf.in_step) {
-                    if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
-                    else status = bdf.pre_step_checks(sys);
-                    work = status == SB_SUCCESS;
+    // the jump at the lower end of interval k < n_t (solver.py:770-781): lamda -= g, optional traces
+    auto jump = [&](int k) {
+        const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) lam[i] -= g[i];
+        if (a.lamda_all || a.quad_all) {
+            const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
+            const bool ok = status == SB_SUCCESS;
+            if (a.lamda_all)
+#pragma unroll
+                for (int i = 0; i < NS; ++i) a.lamda_all[row * NS + i] = ok ? lam[i] : qnan();
+            if (a.quad_all)
+#pragma unroll
+                for (int i = 0; i < ND; ++i) a.quad_all[row * ND + i] = ok ? quad[i] : qnan();
+        }
+    };
+
+    if constexpr (!FLAT) {
+        // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
+        for (int k = k_begin; k < k_end; ++k) {
+            const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
+            const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+            if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
+                // an interval to integrate over needs stored forward steps (none exist when every
+                // output time equals t0: then, as in the reference, only the jumps are applied)
+                if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
+                const bool live = valid && status == SB_SUCCESS;
+                if (live) {
+                    bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
+                    status = bdf.first_call(sys, t_lower);
                 }
-                const unsigned mask = sb_ballot(work);
-                if (mask == 0u) break;
-                if (work) {
-                    const int r = bdf.attempt(sys, mask);
-                    if (r == SB_SUCCESS) {
-                        nloc++;
-                        bdf.snap_to_tstop(sys);
-                        if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
-                        else bdf.limit_to_tstop(sys);
-                    } else if (r != SB_TRY_AGAIN) {
-                        status = r;
+                int nloc = 0;
+                bool reached = false;
+                for (;;) {
+                    bool work = valid && status == SB_SUCCESS && !reached;
+                    if (work && !bdf.in_step) {
+                        if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                        else status = bdf.pre_step_checks(sys);
+                        work = status == SB_SUCCESS;
+                    }
+                    const unsigned mask = sb_ballot(work);
+                    if (mask == 0u) break;
+                    if (work) {
+                        const int r = bdf.attempt(sys, mask);
+                        if (r == SB_SUCCESS) {
+                            nloc++;
+                            bdf.snap_to_tstop(sys);
+                            if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
+                            else bdf.limit_to_tstop(sys);
+                        } else if (r != SB_TRY_AGAIN) {
+                            status = r;
+                        }
                     }
                 }
+                if (valid && status == SB_SUCCESS) {
+                    bdf.get_dky(t_lower, lam);                // CVodeGetB
+                    if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
+                }
             }
-            if (valid && status == SB_SUCCESS) {
-                bdf.get_dky(t_lower, lam);                // CVodeGetB
-                if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
-            }
+            if (valid && k < a.n_t) jump(k);
         }
-        if (k < a.n_t) {
-            const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) lam[i] -= g[i];
-            if (valid && (a.lamda_all || a.quad_all)) {
-                const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
-                const bool ok = status == SB_SUCCESS;
-                if (a.lamda_all)
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) a.lamda_all[row * NS + i] = ok ? lam[i] : qnan();
-                if (a.quad_all)
-#pragma unroll
-                    for (int i = 0; i < ND; ++i) a.quad_all[row * ND + i] = ok ? quad[i] : qnan();
+    } else {
+        // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
+        int k = valid ? k_begin : k_end;    // padding lanes only vote
+        bool fresh = true;                  // between intervals: interval k has not been started yet
+        bool flat = a.flat > 0;
+        int nloc = 0, idle = 0;
+        double t_lower = 0.0;
+        for (;;) {
+            const unsigned m_fresh = sb_ballot(k < k_end && fresh);
+            const unsigned m_step = sb_ballot(k < k_end && !fresh);
+            if ((m_fresh | m_step) == 0u) break;
+            if (m_fresh != 0u) {
+                if (m_step == 0u) {
+                    // a common restart: how long did the lanes of this interval wait for each other?
+                    if (a.flat < 0 && idle > SB_FLAT_IDLE * __popc(m_fresh)) flat = true;
+                    idle = 0;
+                } else {
+                    idle += __popc(m_fresh);
+                }
+            }
+            if (k < k_end && fresh && (flat || m_step == 0u)) {
+                // start intervals until one has to be integrated over
+                while (k < k_end) {
+                    const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
+                    t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+                    if (t_lower < t_upper) {
+                        // an interval to integrate over needs stored forward steps (none exist when
+                        // every output time equals t0: then, as in the reference, only the jumps are
+                        // applied)
+                        if (status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
+                        if (status == SB_SUCCESS) {
+                            bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
+                            status = bdf.first_call(sys, t_lower);
+                            nloc = 0;
+                            fresh = false;
+                            break;
+                        }
+                    }
+                    if (k < a.n_t) jump(k);
+                    ++k;
+                }
+            }
+            // one pass of the step loop for the lanes inside an interval
+            bool work = k < k_end && !fresh && status == SB_SUCCESS;
+            if (work && !bdf.in_step) {
+                if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                else status = bdf.pre_step_checks(sys);
+                work = status == SB_SUCCESS;
+            }
+            const unsigned mask = sb_ballot(work);
+            bool reached = false;
+            if (work) {
+                const int r = bdf.attempt(sys, mask);
+                if (r == SB_SUCCESS) {
+                    nloc++;
+                    bdf.snap_to_tstop(sys);
+                    if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
+                    else bdf.limit_to_tstop(sys);
+                } else if (r != SB_TRY_AGAIN) {
+                    status = r;
+                }
+            }
+            if (k < k_end && !fresh && (reached || status != SB_SUCCESS)) {
+                if (status == SB_SUCCESS) {
+                    bdf.get_dky(t_lower, lam);                // CVodeGetB
+                    if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
+                }
+                if (k < a.n_t) jump(k);
+                ++k;
+                fresh = true;
             }
         }
     }
@@ -470,7 +572,10 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
 }
 
 __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long long inst, bool valid) {
-    backward_unit(a, inst, valid, 0, a.n_t + 1);
+    backward_unit<false>(a, inst, valid, 0, a.n_t + 1);
+}
+__device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, long long inst, bool valid) {
+    backward_unit<true>(a, inst, valid, 0, a.n_t + 1);
 }
 
 }  // namespace sb
@@ -478,15 +583,19 @@ __device__ __forceinline__ void backward_instance(const SbBackwardArgs& a, long 
 #ifndef SB_HOST_EMULATION   // the host emulation calls the *_instance functions directly
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {
-    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    sb::forward_instance(a, inst, inst < a.B);
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long inst = warp * a.lanes + lane;
+    sb::forward_instance(a, inst, lane < a.lanes && inst < a.B);
 }
 
 #if SB_ND > 0
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward_sens(const __grid_constant__ SbForwardArgs a) {
-    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    sb::forward_sens_instance(a, inst, inst < a.B);
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long inst = warp * a.lanes + lane;
+    sb::forward_sens_instance(a, inst, lane < a.lanes && inst < a.B);
 }
 #endif
 
@@ -498,9 +607,10 @@ sb_tables(const SbTablesArgs a) {
     if (inst < a.B) sb::build_table_entry(a, inst, idx);
 }
 
-extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
-sb_backward(const __grid_constant__ SbBackwardArgs a) {
-    // Persistent warps pull work units (group of 32 instances x segment of intervals) from a global
+template <bool FLAT>
+__device__ __forceinline__ void sb_backward_body(const SbBackwardArgs& a) {
+    if (a.steps_total && (*a.steps_total > a.flat_steps) != FLAT) return;   // the other build runs
+    // Persistent warps pull work units (group of a.lanes instances x segment of intervals) from a global
     // counter, in segment-major order.  A solve is ~1700 steps long and the batch is only ~1.7
     // waves of resident warps, so with whole solves as units the second wave leaves a quarter of
     // the machine idle for a full solve time; with short units the idle tail shrinks to one unit
@@ -531,20 +641,27 @@ sb_backward(const __grid_constant__ SbBackwardArgs a) {
             timed_out = __shfl_sync(0xffffffffu, timed_out, 0);
             __threadfence();
         }
-        const long long inst = (long long)grp * 32 + lane;
+        const long long inst = (long long)grp * a.lanes + lane;
+        const bool valid = lane < a.lanes && inst < a.B;
         const int k0 = seg * a.seg_len;
         const int k1 = min(k0 + a.seg_len, a.n_t + 1);
         if (timed_out) {
-            if (inst < a.B) a.carry_i[(size_t)inst * SB_CARRY_INTS] = SB_UNIT_TIMEOUT;
-            if (inst < a.B && k1 == a.n_t + 1) a.status[inst] = SB_UNIT_TIMEOUT;
+            if (valid) a.carry_i[(size_t)inst * SB_CARRY_INTS] = SB_UNIT_TIMEOUT;
+            if (valid && k1 == a.n_t + 1) a.status[inst] = SB_UNIT_TIMEOUT;
         } else {
-            sb::backward_unit(a, inst, inst < a.B, k0, k1);
+            sb::backward_unit<FLAT>(a, inst, valid, k0, k1);
         }
         __threadfence();
         __syncwarp(0xffffffffu);
         if (lane == 0) atomicExch(a.seg_done + grp, seg + 1);
     }
 }
+
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_backward(const __grid_constant__ SbBackwardArgs a) { sb_backward_body<false>(a); }
+
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_backward_flat(const __grid_constant__ SbBackwardArgs a) { sb_backward_body<true>(a); }
 
 extern "C" __global__ void __launch_bounds__(256)
 sb_eval(const SbEvalArgs a) {

@@ -21,6 +21,7 @@ using std::max; using std::min; using std::exp; using std::log; using std::log1p
 
 static inline double __ldg(const double* p) { return *p; }
 static inline int __ldg(const int* p) { return *p; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 
 struct EmuDim { unsigned x, y, z; };

@@ -24,7 +24,7 @@ class ForwardArgs(ctypes.Structure):
                 ('params', _DP), ('atol', _DP), ('y_out', _DP), ('hist', _DP), ('hist_n', _IP),
                 ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong), ('n_t', ctypes.c_int),
                 ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
-                ('sens0_shared', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP), ('tab', _DP)]
+                ('sens0_shared', ctypes.c_int), ('lanes', ctypes.c_int), ('pad_', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP), ('tab', _DP), ('steps_total', ctypes.c_void_p)]
 
 
 class TablesArgs(ctypes.Structure):
@@ -42,7 +42,8 @@ class BackwardArgs(ctypes.Structure):
                 ('grads_shared', ctypes.c_int), ('lamda_all', _DP), ('quad_all', _DP),
                 ('queue', _IP), ('seg_done', _IP), ('carry_d', _DP), ('carry_i', _IP),
                 ('n_seg', ctypes.c_int), ('seg_len', ctypes.c_int), ('n_groups', ctypes.c_int),
-                ('pad2_', ctypes.c_int)]
+                ('lanes', ctypes.c_int), ('flat', ctypes.c_int), ('pad2_', ctypes.c_int),
+                ('steps_total', ctypes.c_void_p), ('flat_steps', ctypes.c_ulonglong)]
 
 
 def _dp(a):
@@ -94,7 +95,7 @@ class Emulator:
         hist_n = np.zeros(B, dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,
-                        max_steps, 0, None, None, _dp(tab))
+                        max_steps, 0, 32, 0, None, None, _dp(tab), None)
         self.lib.emu_forward(ctypes.byref(a))
         return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
                     params=params, tvals=tvals)
@@ -111,13 +112,13 @@ class Emulator:
         status = np.zeros(B, dtype=np.int32)
         stats = np.zeros((B, STATS), dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
-                        None, None, _ip(status), _ip(stats), B, n_t, 0, max_steps, shared,
-                        _dp(sens0), _dp(sens_out), None)
+                        None, None, _ip(status), _ip(stats), B, n_t, 0, max_steps, shared, 32, 0,
+                        _dp(sens0), _dp(sens_out), None, None)
         self.lib.emu_forward_sens(ctypes.byref(a))
         return dict(y=y_out, sens=sens_out, status=status, stats=stats)
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
-                rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000):
+                rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000, flat=None):
         B0 = max(len(np.atleast_2d(y0)), len(np.atleast_2d(params)))
         tab_fused = np.zeros((B0, hist_cap, 10 + 6 * self.ns))
         fwd = self.forward(t0, tvals, y0, params, rtol, atol, hist_cap=hist_cap,
@@ -143,7 +144,7 @@ class Emulator:
                           _dp(fwd['tvals']), _dp(fwd['params']), _dp(grads), _dp(tab),
                           _ip(fwd['hist_n']), _ip(fwd['status']), gptr, _dp(lam_out),
                           _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared, None, None,
-                          None, None, None, None, 1, n_t + 1, 0, 0)
-        self.lib.emu_backward(ctypes.byref(ba))
+                          None, None, None, None, 1, n_t + 1, 0, 32, -1 if flat is None else flat, 0, None, 0)
+        (self.lib.emu_backward if flat is None else self.lib.emu_backward_flat)(ctypes.byref(ba))
         return dict(y=fwd['y'], grad=grad_out, lamda=lam_out, status=status, stats=stats,
                     fwd=fwd, tab=tab)

@@ -24,9 +24,13 @@ void emu_backward(const SbBackwardArgs* a) {
 }
 // one segment of intervals [k0, k1) for every instance (tools/lane_efficiency.py walks a solve
 // interval by interval to read the per-interval counters out of the carry buffers)
+void emu_backward_flat(const SbBackwardArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i) sb::backward_instance_flat(*a, i, true);
+}
 void emu_backward_unit(const SbBackwardArgs* a, int k0, int k1) {
     #pragma omp parallel for schedule(dynamic, 16)
-    for (long long i = 0; i < a->B; ++i) sb::backward_unit(*a, i, true, k0, k1);
+    for (long long i = 0; i < a->B; ++i) sb::backward_unit<false>(*a, i, true, k0, k1);
 }
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
 }

@@ -121,3 +121,21 @@ def test_ten_state_chain_uses_loop_lu(tmp_path):
     assert np.max(np.abs(r['y'] - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
     np.testing.assert_allclose(r['grad'], go, rtol=1e-7)
     np.testing.assert_allclose(r['lamda'], lo, rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['lv_adj', 'robertson_adj'])
+def test_flat_interval_schedule_is_the_same_computation(name, tmp_path):
+    """sb_backward_flat (every lane walks its intervals on its own) performs, per instance, exactly
+    the operations of sb_backward (lanes restart together): bit-identical results and counters."""
+    w = examples.workloads()[name]
+    prob = w.make_problem()
+    B = 8
+    y0, theta = w.draws(B)
+    grads = np.random.default_rng(5).standard_normal((len(w.tvals), prob.n_states))
+    emu = Emulator(prob, str(tmp_path))
+    a = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity)
+    for flat in (0, 1, -1):
+        b = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity,
+                        flat=flat)
+        for key in ('grad', 'lamda', 'status', 'stats'):
+            np.testing.assert_array_equal(a[key], b[key])

@@ -31,7 +31,7 @@ ba = E.BackwardArgs(1e-10, 1e-10, 1e-10, 1e-10, float(w.tvals[-1]), float(w.t0),
                     E._dp(fwd['tvals']), E._dp(fwd['params']), E._dp(g), E._dp(tab),
                     E._ip(fwd['hist_n']), E._ip(fwd['status']), E._dp(grad_out), E._dp(lam_out),
                     E._ip(status), E._ip(stats), B, n_t, cap, 25000, 1, None, None,
-                    None, None, E._dp(carry_d), E._ip(carry_i), n_t + 1, 1, 0, 0)
+                    None, None, E._dp(carry_d), E._ip(carry_i), n_t + 1, 1, 0, 32, -1, 0, None, 0)
 em.lib.emu_backward_unit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 passes = np.zeros((n_t + 1, B), np.int64)
 prev = np.zeros(B, np.int64)
@@ -51,3 +51,43 @@ for lanes in (32, 16, 8, 4):
     whole = tot.sum() / (lanes * tot.max(axis=1).sum())
     print('  %2d lanes/warp: utilisation with a barrier per interval %.3f, without %.3f'
           % (lanes, per_interval, whole))
+
+# ---- restart policies of the flattened backward kernel ------------------------------------------
+# A lane that has finished its interval waits; all waiting lanes restart together (one execution of
+# the divergent restart block, costing R pass-equivalents of warp time) as soon as `need` lanes
+# wait, or the oldest waiter has waited `patience` passes, or nobody is left stepping.
+def simulate(p, need, patience, R=0.3):
+    n_int, n_warp, lanes = p.shape
+    total = 0.0
+    for w in range(n_warp):
+        rem = p[0, w].copy(); k = np.zeros(lanes, int); waited = np.zeros(lanes, int)
+        # intervals with zero passes are skipped without a restart
+        t = 0.0
+        while True:
+            waiting = (rem == 0) & (k < n_int)
+            stepping = rem > 0
+            if not waiting.any() and not stepping.any():
+                break
+            if waiting.any() and (waiting.sum() >= need or waited[waiting].max() >= patience or not stepping.any()):
+                idx = np.nonzero(waiting)[0]
+                k[idx] += 1
+                live = idx[k[idx] < n_int]
+                rem[live] = p[k[live], w, live]
+                waited[idx] = 0
+                if (rem[live] > 0).any():
+                    t += R
+                continue
+            # advance to the next event: the smallest remaining count among stepping lanes
+            adv = rem[stepping].min()
+            if waiting.any():
+                adv = min(adv, max(1, patience - waited[waiting].max()))
+            rem[stepping] -= adv
+            waited[waiting] += adv
+            t += adv
+        total += t
+    return p.sum() / (lanes * total)
+
+if len(sys.argv) > 3:
+    p32 = passes[:, :B // 32 * 32].reshape(n_t + 1, -1, 32)[:, :int(sys.argv[3])]
+    for need, patience in ((32, 10 ** 9), (1, 0), (4, 4), (8, 8), (8, 16), (16, 16), (16, 32), (24, 64)):
+        print('  policy need=%2d patience=%-10d utilisation %.3f' % (need, patience, simulate(p32, need, patience)))
