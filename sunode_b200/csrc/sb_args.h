@@ -9,6 +9,12 @@
 /* history point: (t, order, y[NS])                         -> NS + 2 doubles
  * interpolation table entry for the interval (t_lo, t_hi):
  *   [0] t_lo [1] t_hi [2] order [3] 1/delt [4..9] T[0..5] [10 + NS*j + k] Y[j][k]  -> 10 + 6*NS */
+/* Lanes of a warp that integrate one instance together (sb_group.cuh): one for small systems, a
+ * power-of-two group with one state component per lane from SB_GROUP_MIN_NS states on; beyond 32
+ * states one lane per instance again (loop-based LU in local memory). */
+#define SB_GROUP_MIN_NS 5
+#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 8 ? 8 : (ns) <= 16 ? 16 : (ns) <= 32 ? 32 : 1)
+
 #define SB_HIST_STRIDE(ns) ((ns) + 2)
 #define SB_TAB_STRIDE(ns) (10 + 6 * (ns))
 

@@ -358,21 +358,44 @@ struct Bdf {
     static constexpr int NQ_ = NQ > 0 ? NQ : 1;
     static constexpr bool QUAD = NQ > 0;
 
-    // max over blocks of the weighted RMS norm (one block: the plain WRMS norm)
-    __device__ __forceinline__ double norm(const double* v) const {
-        double r = wrms<NM>(v, ewt);
-#pragma unroll
-        for (int b = 1; b < NBLK; ++b) r = fmax(r, wrms<NM>(v + b * NM, ewt + b * NM));
-        return r;
+    // Lane groups (Sys::GROUP = G > 1): G adjacent lanes of a warp integrate ONE instance together.
+    // Lane r of the group holds component r of every vector (NM = 1; NQ = the quadrature
+    // components r, r + G, ... it owns), row r of the Jacobian and of the Newton matrix; the
+    // scalar controller state (h, q, tau, l, tq, counters ...) is replicated, so the lanes of a
+    // group take every branch together.  What differs from the one-lane-per-instance build is
+    // confined to the hooks below: sums / maxima / votes over the group, and the linear algebra.
+    static constexpr int G = Sys::GROUP;
+    static constexpr int MS = (G > 1) ? Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
+    static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;        // pivot record
+    __device__ __forceinline__ static double gsum(double x) { if constexpr (G > 1) return Sys::gsum(x); else return x; }
+    __device__ __forceinline__ static double gmax(double x) { if constexpr (G > 1) return Sys::gmax(x); else return x; }
+    __device__ __forceinline__ static bool gall(bool b) { if constexpr (G > 1) return Sys::gall(b); else return b; }
+    // mean of the squared weighted components of a state-sized block / of a quadrature vector
+    __device__ __forceinline__ static double ms_y(const double* v, const double* w) {
+        if constexpr (G > 1) { const double x = v[0] * w[0]; return gsum(x * x) * (1.0 / Sys::NS_FULL); }
+        else return wms<NM>(v, w);
     }
+    __device__ __forceinline__ double ms_q(const double* v) const {
+        if constexpr (G > 1) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NQ_; ++i) { const double x = v[i] * ewtQ[i]; s = fma(x, x, s); }
+            return gsum(s) * (1.0 / Sys::NQ_FULL);
+        } else return wms<NQ_>(v, ewtQ);
+    }
+    __device__ __forceinline__ static bool finite_y(const double* v) { return gall(all_finite<N>(v)); }
+    __device__ __forceinline__ static bool finite_q(const double* v) { return gall(all_finite<NQ_>(v)); }
+
+    // max over blocks of the weighted RMS norm (one block: the plain WRMS norm)
+    __device__ __forceinline__ double norm(const double* v) const { return sb_sqrt(norm2(v)); }
     // Its square.  Every test a step makes on a norm (Newton convergence, error test, tolsf) and
     // the step-size ratios are monotone in the norm, so the step loop works on squares throughout
     // and takes no square roots (names ending in 2: del2, delp2, crate2, acnrm2, dsm2; tq[1..4]
     // hold the squares of CVODES' test quantities).  Only cvHin still needs norms proper.
     __device__ __forceinline__ double norm2(const double* v) const {
-        double r = wms<NM>(v, ewt);
+        double r = ms_y(v, ewt);
 #pragma unroll
-        for (int b = 1; b < NBLK; ++b) r = fmax(r, wms<NM>(v + b * NM, ewt + b * NM));
+        for (int b = 1; b < NBLK; ++b) r = fmax(r, ms_y(v + b * NM, ewt + b * NM));
         return r;
     }
 
@@ -387,8 +410,8 @@ struct Bdf {
     int q, qprime, qwait, L, qu;
     bool jcur;
     // linear solver
-    double savedJ[NM * NM], M[NM * NM];
-    int piv[NM];
+    double savedJ[MS], M[MS];
+    int piv[PS];
     // counters
     int nst, nstlp, nstlj;
     Stats st;
@@ -447,7 +470,7 @@ struct Bdf {
                 ewtQ[i] = sb_div(1.0, d);
             }
         }
-        return ok;
+        return gall(ok);
     }
 
     // ------------------------------------------------------------------ first step: cvHin
@@ -457,7 +480,7 @@ struct Bdf {
         for (int i = 0; i < N; ++i) y[i] = fma(hg, zn[1][i], zn[0][i]);
         sys.set_time(tn + hg);
         sys.rhs(y, f); st.nfe++;
-        if (!all_finite<N>(f)) return 1;
+        if (!finite_y(f)) return 1;
         const double rhg = sb_div(1.0, hg);
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = (f[i] - zn[1][i]) * rhg;
@@ -465,10 +488,10 @@ struct Bdf {
         if (QUAD) {
             double fq[NQ_];
             sys.quad(y, fq);
-            if (!all_finite<NQ_>(fq)) return 1;
+            if (!finite_q(fq)) return 1;
 #pragma unroll
             for (int i = 0; i < NQ_; ++i) fq[i] = (fq[i] - znQ[1][i]) * rhg;
-            nrm = fmax(nrm, wrms<NQ_>(fq, ewtQ));
+            nrm = fmax(nrm, sb_sqrt(ms_q(fq)));
         }
         *yddnrm = nrm;
         return 0;
@@ -497,6 +520,7 @@ struct Bdf {
                 hub_inv = fmax(hub_inv, sb_div(fabs(znQ[1][i]), d));
             }
         }
+        hub_inv = gmax(hub_inv);
         double hub = HUB_FACTOR * tdist;
         if (hub * hub_inv > 1.0) hub = sb_div(1.0, hub_inv);
         double hg = sb_sqrt(hlb * hub);
@@ -534,10 +558,10 @@ struct Bdf {
         if (!set_ewt(sys)) return SB_ILL_INPUT;
         sys.set_time(tn);
         sys.rhs(zn[0], zn[1]); st.nfe++;
-        if (!all_finite<N>(zn[1])) return SB_FIRST_RHSFUNC_ERR;
+        if (!finite_y(zn[1])) return SB_FIRST_RHSFUNC_ERR;
         if (QUAD) {
             sys.quad(zn[0], znQ[1]);
-            if (!all_finite<NQ_>(znQ[1])) return SB_RHSFUNC_FAIL;
+            if (!finite_q(znQ[1])) return SB_RHSFUNC_FAIL;
         }
         if (Sys::TSTOP && (sys.tstop() - tn) * (tout - tn) <= 0.0) return SB_ILL_INPUT;
         double tout_hin = tout;
@@ -732,13 +756,13 @@ struct Bdf {
             double f[N];
             sys.set_time(tn);
             sys.rhs(zn[0], f); st.nfe++;
-            if (!all_finite<N>(f)) ret = SB_UNREC_RHSFUNC_ERR;
+            if (!finite_y(f)) ret = SB_UNREC_RHSFUNC_ERR;
 #pragma unroll
             for (int i = 0; i < N; ++i) zn[1][i] = h * f[i];
             if (QUAD) {
                 double fq[NQ_];
                 sys.quad(zn[0], fq);
-                if (!all_finite<NQ_>(fq)) ret = SB_RHSFUNC_FAIL;
+                if (!finite_q(fq)) ret = SB_RHSFUNC_FAIL;
 #pragma unroll
                 for (int i = 0; i < NQ_; ++i) znQ[1][i] = h * fq[i];
             }
@@ -823,15 +847,20 @@ struct Bdf {
         if (jbad) {
             st.nje++; nstlj = nst; jcur = true;
             sys.jac(ypred, savedJ);
-            if (!all_finite<NM * NM>(savedJ)) return 1;
+            if (!gall(all_finite<MS>(savedJ))) return 1;
         } else {
             jcur = false;
         }
 #pragma unroll
-        for (int k = 0; k < NM * NM; ++k) M[k] = -gamma * savedJ[k];
+        for (int k = 0; k < MS; ++k) M[k] = -gamma * savedJ[k];
+        if constexpr (G > 1) {
+            Sys::add_identity(M);
+            return Sys::lu_factor(M, piv) ? 0 : 1;
+        } else {
 #pragma unroll
-        for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
-        return lu_factor<NM>(M, piv) ? 0 : 1;
+            for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
+            return lu_factor<NM>(M, piv) ? 0 : 1;
+        }
     }
 
     // ------------------------------------------------------------------ nonlinear solve
@@ -855,7 +884,7 @@ struct Bdf {
                 for (int i = 0; i < N; ++i) { acor[i] = 0.0; ycur[i] = zn[0][i]; }
                 sys.rhs(ycur, f); st.nfe++;
                 // a failure before the Newton loop (residual or setup) is returned without a retry
-                if (!all_finite<N>(f)) { done = true; live = false; }
+                if (!finite_y(f)) { done = true; live = false; }
             }
             if (live && callSetup) {
                 const int r = lsetup(sys, convfail, ycur);
@@ -875,7 +904,10 @@ struct Bdf {
                 if (run) {
                     st.nni++;
 #pragma unroll
-                    for (int b = 0; b < NBLK; ++b) lu_solve<NM>(M, piv, delta + b * NM);
+                    for (int b = 0; b < NBLK; ++b) {
+                        if constexpr (G > 1) Sys::lu_solve(M, piv, delta + b * NM);
+                        else lu_solve<NM>(M, piv, delta + b * NM);
+                    }
                     if (gamrat != 1.0) {
                         const double sc = sb_div(2.0, 1.0 + gamrat);
 #pragma unroll
@@ -900,7 +932,7 @@ struct Bdf {
                             run = false;
                         } else {
                             sys.rhs(ycur, f); st.nfe++;
-                            if (!all_finite<N>(f)) run = false;
+                            if (!finite_y(f)) run = false;
 #pragma unroll
                             for (int i = 0; i < N; ++i)
                                 delta[i] = fma(gamma, f[i], -fma(rl1, zn[1][i], acor[i]));
@@ -980,7 +1012,7 @@ struct Bdf {
                 for (int i = 0; i < NQ_; ++i) zqQ[i] = is_q ? znQ[j][i] : zqQ[i];
             });
             double ddn2 = norm2(zq);
-            if (QUAD) ddn2 = fmax(ddn2, wms<NQ_>(zqQ, ewtQ));
+            if (QUAD) ddn2 = fmax(ddn2, ms_q(zqQ));
             ddn2 *= tq[1];
             etaqm1 = eta_root2((BIAS1 * BIAS1) * ddn2, q);
         }
@@ -998,7 +1030,7 @@ struct Bdf {
                 double tmpq[NQ_];
 #pragma unroll
                 for (int i = 0; i < NQ_; ++i) tmpq[i] = fma(-cquot, zsaveQ[i], acorQ[i]);
-                dup2 = fmax(dup2, wms<NQ_>(tmpq, ewtQ));
+                dup2 = fmax(dup2, ms_q(tmpq));
             }
             dup2 *= tq[3];
             etaqp1 = eta_root2((BIAS3 * BIAS3) * dup2, L + 1);
@@ -1101,7 +1133,7 @@ struct Bdf {
                 ncf = 0; nef = 0;
                 double fq[NQ_];
                 sys.quad(ycur, fq);
-                if (!all_finite<NQ_>(fq)) {
+                if (!finite_q(fq)) {
                     st.ncfn++; ncf++;
                     etamax = 1.0;
                     go = false;
@@ -1115,7 +1147,7 @@ struct Bdf {
                 } else {
 #pragma unroll
                     for (int i = 0; i < NQ_; ++i) acorQ[i] = rl1 * fma(h, fq[i], -znQ[1][i]);
-                    const double dsmQ2 = wms<NQ_>(acorQ, ewtQ) * tq[2];
+                    const double dsmQ2 = ms_q(acorQ) * tq[2];
                     if (!(dsmQ2 <= 1.0)) {
                         nefQ++;
                         nflag = PREV_ERR_FAIL;
@@ -1168,10 +1200,8 @@ struct Bdf {
     __device__ __forceinline__ int pre_step_checks(const Sys& sys) {
         if (nst > 0 && !set_ewt(sys)) return SB_ILL_INPUT;
         // tolsf = uround * ||y||_wrms > 1, tested on the squares (no square roots needed)
-        double nrm2 = wms<NM>(zn[0], ewt);
-#pragma unroll
-        for (int b = 1; b < NBLK; ++b) nrm2 = fmax(nrm2, wms<NM>(zn[0] + b * NM, ewt + b * NM));
-        if (QUAD) nrm2 = fmax(nrm2, wms<NQ_>(znQ[0], ewtQ));
+        double nrm2 = norm2(zn[0]);
+        if (QUAD) nrm2 = fmax(nrm2, ms_q(znQ[0]));
         if ((SB_UROUND * SB_UROUND) * nrm2 > 1.0) return SB_TOO_MUCH_ACC;
         return SB_SUCCESS;
     }

@@ -1,0 +1,336 @@
+// sb_group.cuh -- lane groups: G adjacent lanes of a warp integrate ONE instance together.
+//
+// For systems of more than a few states the one-lane-per-instance build runs out of registers: the
+// 8-state SEIR adjoint keeps ~2.5 kB of integrator state per instance, the compiler spills 2 kB of
+// it per thread, the unrolled 8x8 LU select network alone is 280 kB of code, and ncu shows the
+// kernel waiting on local-memory loads (37 % of the stall samples) and instruction fetch (35 %).
+// Here lane r of a group holds component r of every vector, row r of the Jacobian and of the
+// Newton matrix I - gamma*J; the dense LU (partial pivoting, implicit row exchange) and its
+// triangular solves run across the lanes with warp shuffles, norms are butterfly sums, and the
+// scalar controller state is replicated so that the lanes of a group branch together.  The
+// algorithm -- CVODES' BDF as the reference reaches it through lib.CVodeB
+// (/root/reference/sunode/solver.py:756-760) -- is the one of sb_bdf.cuh: this file only supplies
+// the hooks `Bdf` calls when Sys::GROUP > 1 and the backward driver for grouped lanes.
+#pragma once
+
+namespace sb {
+
+template <int G>
+struct LaneGroup {
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    __device__ __forceinline__ static int rank() { return (int)(threadIdx.x & (G - 1)); }
+    __device__ __forceinline__ static unsigned mask() {
+        if constexpr (G == 32) return 0xffffffffu;
+        else return ((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+    }
+    __device__ __forceinline__ static double bcast(double x, int src) { return __shfl_sync(mask(), x, src, G); }
+    __device__ __forceinline__ static double sum(double x) {
+        // xor butterfly: every lane ends with the bitwise identical sum
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask(), x, o, G);
+        return x;
+    }
+    __device__ __forceinline__ static double max(double x) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(mask(), x, o, G));
+        return x;
+    }
+    __device__ __forceinline__ static bool all(bool b) { return __all_sync(mask(), b) != 0; }
+
+    // register array element `rank` (0 for lanes past the end) without dynamic indexing
+    template <int N_>
+    __device__ __forceinline__ static double pick(const double* v, int idx) {
+        double r = 0.0;
+        static_for<0, N_>([&](auto J_) { constexpr int j = SB_IDX(J_); r = (idx == j) ? v[j] : r; });
+        return r;
+    }
+
+    // ---- dense LU across the lanes: lane r < N_ holds row r of the matrix in m[0..N_-1] ---------
+    // Partial pivoting without moving rows: piv[k] is the lane whose row is the k-th pivot row.
+    // After the factorisation a lane pivoted at step s holds the multipliers of steps < s in
+    // m[0..s-1], the RECIPROCAL pivot in m[s] and its U entries in m[s+1..].
+    template <int N_>
+    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) {
+        const int r = rank();
+        bool ok = true;
+        bool used = r >= N_;                       // padding lanes hold no row
+        static_for<0, N_>([&](auto K_) {
+            constexpr int k = SB_IDX(K_);
+            double cand = used ? -1.0 : fabs(m[k]);
+            int who = r;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const double oc = __shfl_xor_sync(mask(), cand, o, G);
+                const int ow = __shfl_xor_sync(mask(), who, o, G);
+                const bool take = (oc > cand) || (oc == cand && ow < who);
+                cand = take ? oc : cand;
+                who = take ? ow : who;
+            }
+            piv[k] = who;
+            if (!(cand > 0.0)) ok = false;
+            const double rp = sb_div(1.0, bcast(m[k], who));
+            const bool me = (r == who);
+            const bool elim = !used && !me;
+            const double mult = m[k] * rp;
+            static_for<k + 1, N_>([&](auto J_) {
+                constexpr int j = SB_IDX(J_);
+                const double pj = bcast(m[j], who);
+                m[j] = elim ? fma(-mult, pj, m[j]) : m[j];
+            });
+            m[k] = elim ? mult : (me ? rp : m[k]);
+            used = used || me;
+        });
+        return ok;
+    }
+
+    // b[0]: entry `rank` of the right-hand side on entry, of the solution on return
+    template <int N_>
+    __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
+        const int r = rank();
+        int mystep = -1;                           // padding lanes: none
+        static_for<0, N_>([&](auto K_) { constexpr int k = SB_IDX(K_); mystep = (piv[k] == r) ? k : mystep; });
+        double v = b[0];
+        static_for<0, N_>([&](auto K_) {           // L y = P b
+            constexpr int k = SB_IDX(K_);
+            const double vk = bcast(v, piv[k]);
+            v = (mystep > k) ? fma(-m[k], vk, v) : v;
+        });
+        double x = 0.0;
+        static_for<0, N_>([&](auto K_) {           // U x = y
+            constexpr int k = N_ - 1 - SB_IDX(K_);
+            const double xk = bcast(v * m[k], piv[k]);
+            v = (mystep >= 0 && mystep < k) ? fma(-m[k], xk, v) : v;
+            x = (r == k) ? xk : x;
+        });
+        b[0] = x;
+    }
+};
+
+// ------------------------------------------------------------------------------------ backward
+template <int G>
+struct BwdSysG {
+    using LG = LaneGroup<G>;
+    static constexpr bool TSTOP = true;
+    static constexpr int GROUP = G, NS_FULL = NS, NQ_FULL = ND_;
+    static constexpr int NQL = (ND + G - 1) / G > 0 ? (ND + G - 1) / G : 1;   // quadrature components per lane
+    static_assert(NS <= G, "one state component per lane");
+    const SbBackwardArgs& a;
+    __device__ __forceinline__ explicit BwdSysG(const SbBackwardArgs& a_) : a(a_) {}
+    __device__ __forceinline__ double rtol() const { return a.rtol; }
+    __device__ __forceinline__ double atol(int) const { return a.atol; }
+    __device__ __forceinline__ double rtolQ() const { return a.rtol_q; }
+    __device__ __forceinline__ double atolQ() const { return a.atol_q; }
+    __device__ __forceinline__ double tstop() const { return a.t_end; }
+    __device__ __forceinline__ static double gsum(double x) { return LG::sum(x); }
+    __device__ __forceinline__ static double gmax(double x) { return LG::max(x); }
+    __device__ __forceinline__ static bool gall(bool b) { return LG::all(b); }
+    __device__ __forceinline__ static void add_identity(double* m) {
+        const int r = LG::rank();
+        static_for<0, NS>([&](auto J_) { constexpr int j = SB_IDX(J_); m[j] += (r == j) ? 1.0 : 0.0; });
+    }
+    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) { return LG::template lu_factor<NS>(m, piv); }
+    __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
+        LG::template lu_solve<NS>(m, piv, b);
+    }
+
+    double p[NP_];
+    const double* tab;     // this instance's table base
+    int np;                // stored points; intervals are 1 .. np-1
+    int idx;               // current interval (CVODES' ilast)
+    double t;
+    double yi[NS];         // forward solution interpolated at t (all components, in every lane)
+
+    // as BwdSys::set_time; the lanes of a group share t and idx, read the knots together (one
+    // broadcast load) and one column of the divided differences each (one 8*NS-byte segment per
+    // row and group), then exchange the interpolated components
+    __device__ __forceinline__ void set_time(double t_) {
+        t = t_;
+        const int r = LG::rank();
+        const int col = r < NS ? r : 0;
+        const double* e = tab + (size_t)idx * TAB_STRIDE;
+        double lo, hi, inv_delt, T[SB_QMAX], Y[SB_LMAX];
+        int order;
+        bool went_left = false;
+#pragma unroll 1
+        for (;;) {
+            lo = __ldg(e); hi = __ldg(e + 1);
+            order = (int)__ldg(e + 2);
+            inv_delt = __ldg(e + 3);
+#pragma unroll
+            for (int i = 0; i < SB_QMAX; ++i) T[i] = __ldg(e + 4 + i);
+#pragma unroll
+            for (int j = 0; j < SB_LMAX; ++j) Y[j] = __ldg(e + 10 + NS * j + col);
+            // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
+            if ((t < lo || (went_left && t <= lo)) && idx > 1) { --idx; e -= TAB_STRIDE; went_left = true; }
+            else if (t > hi && idx < np - 1 && !went_left) { ++idx; e += TAB_STRIDE; }
+            else break;
+        }
+        double mine = Y[0];
+        double c = 1.0;
+#pragma unroll
+        for (int i = 0; i < SB_QMAX; ++i) {
+            c = (i < order) ? c * ((t - T[i]) * inv_delt) : 0.0;
+            mine = fma(c, Y[i + 1], mine);
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) yi[j] = LG::bcast(mine, j);
+    }
+    __device__ __forceinline__ void gather(const double* mine, double* full) const {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) full[j] = LG::bcast(mine[0], j);
+    }
+    // every lane evaluates the whole (cheap) function and keeps its own component
+    __device__ __forceinline__ void rhs(const double* lam_mine, double* out_mine) const {
+        double lam[NS], out[NS];
+        gather(lam_mine, lam);
+        sb_adj_rhs(t, yi, lam, p, out);
+        out_mine[0] = LG::template pick<NS>(out, LG::rank());
+    }
+    __device__ __forceinline__ void jac(const double*, double* Jrow) const {
+        double J[NS * NS];
+        sb_adj_jac(t, yi, p, J);
+        const int r = LG::rank();
+        static_for<0, NS>([&](auto J_) {
+            constexpr int j = SB_IDX(J_);
+            Jrow[j] = LG::template pick<NS>(J + NS * j, r);     // column-major: J[r + NS*j]
+        });
+    }
+    __device__ __forceinline__ void quad(const double* lam_mine, double* out_mine) const {
+        double lam[NS], out[ND_];
+        gather(lam_mine, lam);
+#pragma unroll
+        for (int i = 0; i < ND_; ++i) out[i] = 0.0;
+        sb_quad_rhs(t, yi, lam, p, out);
+#pragma unroll
+        for (int c = 0; c < NQL; ++c) out_mine[c] = LG::template pick<ND_>(out, LG::rank() + G * c);
+    }
+};
+
+// The backward driver of kernels.cuh (backward_unit<false>: lanes walk the intervals together) for
+// grouped lanes.  `inst` / `valid` are per group; a lane owns lamda[rank] and the quadrature
+// components rank, rank + G, ...
+template <int G>
+__device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, long long inst, bool valid,
+                                                    int k_begin, int k_end) {
+    using Sys = BwdSysG<G>;
+    using LG = LaneGroup<G>;
+    constexpr int NQL = Sys::NQL;
+    using Integrator = Bdf<1, (ND > 0 ? NQL : 0), Sys>;
+    if (!valid) inst = 0;
+    const int r = LG::rank();
+    const bool has_y = r < NS;
+    const bool first = k_begin == 0, last = k_end == a.n_t + 1;
+    const int np = a.hist_n[inst];
+
+    Integrator bdf;
+    Sys sys(a);
+    double lam[1], quad[NQL];
+    int status;
+    bdf.clear_stats();
+    sys.idx = np > 1 ? np - 1 : 1;
+    if (first) {
+        status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
+        lam[0] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NQL; ++c) quad[c] = 0.0;
+    } else {
+        const double* cd = a.carry_d + (size_t)inst * (NS + ND_);
+        const int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
+        lam[0] = has_y ? cd[r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NQL; ++c) quad[c] = (r + G * c < ND) ? cd[NS + r + G * c] : 0.0;
+        status = ci[0]; sys.idx = ci[1];
+        bdf.st.nst = ci[2]; bdf.st.nfe = ci[3]; bdf.st.nje = ci[4]; bdf.st.nsetups = ci[5];
+        bdf.st.netf = ci[6]; bdf.st.ncfn = ci[7]; bdf.st.nni = ci[8];
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+    sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
+    sys.np = np;
+    sys.t = 0.0;
+    bdf.reinit(a.t_start, lam, quad);
+
+    const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
+    for (int k = k_begin; k < k_end; ++k) {
+        const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
+        const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+        if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
+            if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
+            const bool live = valid && status == SB_SUCCESS;
+            if (live) {
+                bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
+                status = bdf.first_call(sys, t_lower);
+            }
+            int nloc = 0;
+            bool reached = false;
+            for (;;) {
+                bool work = valid && status == SB_SUCCESS && !reached;
+                if (work && !bdf.in_step) {
+                    if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                    else status = bdf.pre_step_checks(sys);
+                    work = status == SB_SUCCESS;
+                }
+                const unsigned mask = sb_ballot(work);
+                if (mask == 0u) break;
+                if (work) {
+                    const int rr = bdf.attempt(sys, mask);
+                    if (rr == SB_SUCCESS) {
+                        nloc++;
+                        bdf.snap_to_tstop(sys);
+                        if ((bdf.tn - t_lower) * bdf.h >= 0.0) reached = true;
+                        else bdf.limit_to_tstop(sys);
+                    } else if (rr != SB_TRY_AGAIN) {
+                        status = rr;
+                    }
+                }
+            }
+            if (valid && status == SB_SUCCESS) {
+                bdf.get_dky(t_lower, lam);                // CVodeGetB
+                if (ND > 0) bdf.get_quad(t_lower, quad);  // CVodeGetQuadB, carried into the next interval
+            }
+        }
+        if (valid && k < a.n_t) {
+            const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
+            if (has_y) lam[0] -= g[r];
+            if (a.lamda_all || a.quad_all) {
+                const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
+                const bool ok = status == SB_SUCCESS;
+                if (a.lamda_all && has_y) a.lamda_all[row * NS + r] = ok ? lam[0] : qnan();
+                if (a.quad_all)
+#pragma unroll
+                    for (int c = 0; c < NQL; ++c)
+                        if (r + G * c < ND) a.quad_all[row * ND + r + G * c] = ok ? quad[c] : qnan();
+            }
+        }
+    }
+    if (!valid) return;
+    if (!last) {
+        double* cd = a.carry_d + (size_t)inst * (NS + ND_);
+        int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
+        if (has_y) cd[r] = lam[0];
+#pragma unroll
+        for (int c = 0; c < NQL; ++c)
+            if (r + G * c < ND) cd[NS + r + G * c] = quad[c];
+        if (r == 0) {
+            ci[0] = status; ci[1] = sys.idx;
+            ci[2] = bdf.st.nst; ci[3] = bdf.st.nfe; ci[4] = bdf.st.nje; ci[5] = bdf.st.nsetups;
+            ci[6] = bdf.st.netf; ci[7] = bdf.st.ncfn; ci[8] = bdf.st.nni;
+        }
+        return;
+    }
+    const bool bad = status != SB_SUCCESS;
+    if (has_y) a.lamda_out[inst * NS + r] = bad ? qnan() : lam[0];
+#pragma unroll
+    for (int c = 0; c < NQL; ++c)
+        if (r + G * c < ND) a.grad_out[inst * ND + r + G * c] = bad ? qnan() : quad[c];
+    if (r == 0) {
+        a.status[inst] = status;
+        if (a.stats) {
+            int* s = a.stats + inst * SB_STATS_STRIDE;
+            s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+            s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = np;
+        }
+    }
+}
+
+}  // namespace sb

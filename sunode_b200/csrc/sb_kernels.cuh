@@ -36,6 +36,11 @@ constexpr int NP = SB_NP;
 constexpr int ND = SB_ND;
 constexpr int NP_ = SB_NP > 0 ? SB_NP : 1;
 constexpr int ND_ = SB_ND > 0 ? SB_ND : 1;
+#if defined(SB_NO_GROUP) || defined(SB_HOST_EMULATION)
+constexpr int GROUP = 1;
+#else
+constexpr int GROUP = SB_GROUP_SIZE(SB_NS);
+#endif
 constexpr int HIST_STRIDE = SB_HIST_STRIDE(SB_NS);
 constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
 
@@ -48,6 +53,7 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000
 template <int NBLK>
 struct FwdSysT {
     static constexpr bool TSTOP = false;
+    static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = 1;
     const SbForwardArgs& a;
     double p[NP_];
     double t;
@@ -262,6 +268,7 @@ __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long lo
 // ------------------------------------------------------------------------------------ backward
 struct BwdSys {
     static constexpr bool TSTOP = true;
+    static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = ND_;
     const SbBackwardArgs& a;
     __device__ __forceinline__ explicit BwdSys(const SbBackwardArgs& a_) : a(a_) {}
     __device__ __forceinline__ double rtol() const { return a.rtol; }
@@ -581,6 +588,11 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
 }  // namespace sb
 
 #ifndef SB_HOST_EMULATION   // the host emulation calls the *_instance functions directly
+#include "sb_group.cuh"
+
+// read by the launcher (instances per warp of the backward kernels = 32 / sb_group_size)
+__device__ int sb_group_size = sb::GROUP;
+
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {
     const int lane = threadIdx.x & 31;
@@ -641,13 +653,19 @@ __device__ __forceinline__ void sb_backward_body(const SbBackwardArgs& a) {
             timed_out = __shfl_sync(0xffffffffu, timed_out, 0);
             __threadfence();
         }
-        const long long inst = (long long)grp * a.lanes + lane;
-        const bool valid = lane < a.lanes && inst < a.B;
+        // a.lanes instances per warp: one per lane, or one per group of sb::GROUP lanes
+        const int slot = lane / sb::GROUP;
+        const long long inst = (long long)grp * a.lanes + slot;
+        const bool valid = slot < a.lanes && inst < a.B;
+        const bool writer = (lane % sb::GROUP) == 0;
         const int k0 = seg * a.seg_len;
         const int k1 = min(k0 + a.seg_len, a.n_t + 1);
         if (timed_out) {
-            if (valid) a.carry_i[(size_t)inst * SB_CARRY_INTS] = SB_UNIT_TIMEOUT;
-            if (valid && k1 == a.n_t + 1) a.status[inst] = SB_UNIT_TIMEOUT;
+            if (valid && writer) a.carry_i[(size_t)inst * SB_CARRY_INTS] = SB_UNIT_TIMEOUT;
+            if (valid && writer && k1 == a.n_t + 1) a.status[inst] = SB_UNIT_TIMEOUT;
+        } else if constexpr (sb::GROUP > 1) {
+            // grouped lanes: both builds run the common-restart schedule
+            sb::backward_unit_group<sb::GROUP>(a, inst, valid, k0, k1);
         } else {
             sb::backward_unit<FLAT>(a, inst, valid, k0, k1);
         }
