@@ -346,6 +346,38 @@ struct Stats {
     int nst, nfe, nje, nsetups, netf, ncfn, nni;
 };
 
+// Fixed-size array with value semantics (so that it can be a member that is either held by value
+// or bound by reference, see Bdf::Mem); indices are literals after unrolling, as for plain arrays.
+template <class T, int N_>
+struct Arr {
+    T v[N_];
+    __device__ __forceinline__ T& operator[](int i) { return v[i]; }
+    __device__ __forceinline__ const T& operator[](int i) const { return v[i]; }
+};
+
+// The per-INSTANCE part of the integrator state: everything that is not a vector component.  With
+// one lane per instance it lives in that lane's registers (`Bdf` holds these members by value);
+// with a group of lanes per instance it is stored once per group in shared memory and `Bdf` binds
+// its members to it by reference -- replicated in every lane's registers it would cost ~110
+// registers per lane and cap the kernel at 8 warps (32 instances) per SM.
+template <int PS>
+struct BdfCtl {
+    Arr<double, SB_LMAX + 1> tau;
+    Arr<double, SB_LMAX> l;
+    Arr<double, 6> tq;
+    double h, hprime, hscale, eta, etamax, tn, hu;
+    double rl1, gamma, gammap, gamrat, crate2, delp2, acnrm2, saved_tq5;
+    double step_t0;
+    Arr<int, PS> piv;
+    int q, qprime, qwait, L, qu;
+    int nst, nstlp, nstlj;
+    Stats st;
+    int ncf, nef, nefQ, nflag, pend;
+    bool jcur, in_step;
+};
+template <bool REF, class T> struct MemT { using type = T; };
+template <class T> struct MemT<true, T> { using type = T&; };
+
 // NM = dimension of the ODE (and of the Newton matrix), NBLK = number of NM-sized blocks that are
 // integrated together: 1 for a plain solve, 1 + n_sens for CVODES' simultaneous forward
 // sensitivity analysis, where block 0 is y and block 1 + k the sensitivity dy/dp_k.  All blocks
@@ -403,28 +435,43 @@ struct Bdf {
     double zn[SB_LMAX][N], zsave[N], acor[N], ewt[N];
     double znQ[SB_LMAX][NQ_], zsaveQ[NQ_], acorQ[NQ_], ewtQ[NQ_];
     double ycur[N];                 // zn[0] + acor after the nonlinear solve
+    // per-instance state: by value (registers) with one lane per instance, references into the
+    // group's shared-memory record otherwise (see BdfCtl)
+    using Ctl = BdfCtl<PS>;
+    template <class T> using Mem = typename MemT<(G > 1), T>::type;
     // step / order control
-    double tau[SB_LMAX + 1], l[SB_LMAX], tq[6];
-    double h, hprime, hscale, eta, etamax, tn, hu;
-    double rl1, gamma, gammap, gamrat, crate2, delp2, acnrm2, saved_tq5;
-    int q, qprime, qwait, L, qu;
-    bool jcur;
+    Mem<Arr<double, SB_LMAX + 1>> tau;
+    Mem<Arr<double, SB_LMAX>> l;
+    Mem<Arr<double, 6>> tq;
+    Mem<double> h, hprime, hscale, eta, etamax, tn, hu;
+    Mem<double> rl1, gamma, gammap, gamrat, crate2, delp2, acnrm2, saved_tq5;
+    Mem<int> q, qprime, qwait, L, qu;
+    Mem<bool> jcur;
     // linear solver
     double savedJ[MS], M[MS];
-    int piv[PS];
+    Mem<Arr<int, PS>> piv;
     // counters
-    int nst, nstlp, nstlj;
-    Stats st;
+    Mem<int> nst, nstlp, nstlj;
+    Mem<Stats> st;
     // a step in flight (cvStep's locals): one call of attempt() is one pass of cvStep's retry loop,
     // so that the lanes of a warp can be re-converged between passes by the caller
-    double step_t0;
-    int ncf, nef, nefQ, nflag;
-    bool in_step;
+    Mem<double> step_t0;
+    Mem<int> ncf, nef, nefQ, nflag;
+    Mem<bool> in_step;
     // History manipulations requested by the previous pass (failed pass: restore + rescale, maybe
     // an order drop; new step with a new step size: rescale, maybe an order change).  They are
     // carried out at ONE place, the top of the next attempt(), so that the bulky restore /
     // rescale / order-change code exists once instead of once per failure branch.
-    int pend;
+    Mem<int> pend;
+
+    __device__ __forceinline__ explicit Bdf(Ctl& c)
+        : tau(c.tau), l(c.l), tq(c.tq), h(c.h), hprime(c.hprime), hscale(c.hscale), eta(c.eta),
+          etamax(c.etamax), tn(c.tn), hu(c.hu), rl1(c.rl1), gamma(c.gamma), gammap(c.gammap),
+          gamrat(c.gamrat), crate2(c.crate2), delp2(c.delp2), acnrm2(c.acnrm2),
+          saved_tq5(c.saved_tq5), q(c.q), qprime(c.qprime), qwait(c.qwait), L(c.L), qu(c.qu),
+          jcur(c.jcur), piv(c.piv), nst(c.nst), nstlp(c.nstlp), nstlj(c.nstlj), st(c.st),
+          step_t0(c.step_t0), ncf(c.ncf), nef(c.nef), nefQ(c.nefQ), nflag(c.nflag),
+          in_step(c.in_step), pend(c.pend) {}
 
     // ------------------------------------------------------------------ (re)initialisation
     // CVodeReInit (+ CVodeQuadReInit): order 1, fresh controller state, counters cleared
@@ -855,11 +902,11 @@ struct Bdf {
         for (int k = 0; k < MS; ++k) M[k] = -gamma * savedJ[k];
         if constexpr (G > 1) {
             Sys::add_identity(M);
-            return Sys::lu_factor(M, piv) ? 0 : 1;
+            return Sys::lu_factor(M, piv.v) ? 0 : 1;
         } else {
 #pragma unroll
             for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
-            return lu_factor<NM>(M, piv) ? 0 : 1;
+            return lu_factor<NM>(M, piv.v) ? 0 : 1;
         }
     }
 
@@ -905,8 +952,8 @@ struct Bdf {
                     st.nni++;
 #pragma unroll
                     for (int b = 0; b < NBLK; ++b) {
-                        if constexpr (G > 1) Sys::lu_solve(M, piv, delta + b * NM);
-                        else lu_solve<NM>(M, piv, delta + b * NM);
+                        if constexpr (G > 1) Sys::lu_solve(M, piv.v, delta + b * NM);
+                        else lu_solve<NM>(M, piv.v, delta + b * NM);
                     }
                     if (gamrat != 1.0) {
                         const double sc = sb_div(2.0, 1.0 + gamrat);

@@ -133,12 +133,12 @@ struct BwdSysG {
         LG::template lu_solve<NS>(m, piv, b);
     }
 
-    double p[NP_];
+    const double* p;       // this instance's parameters (global memory, read where needed)
     const double* tab;     // this instance's table base
     int np;                // stored points; intervals are 1 .. np-1
     int idx;               // current interval (CVODES' ilast)
     double t;
-    double yi[NS];         // forward solution interpolated at t (all components, in every lane)
+    double* yi;            // forward solution interpolated at t: the group's [NS] shared-memory slot
 
     // as BwdSys::set_time; the lanes of a group share t and idx, read the knots together (one
     // broadcast load) and one column of the divided differences each (one 8*NS-byte segment per
@@ -172,8 +172,9 @@ struct BwdSysG {
             c = (i < order) ? c * ((t - T[i]) * inv_delt) : 0.0;
             mine = fma(c, Y[i + 1], mine);
         }
-#pragma unroll
-        for (int j = 0; j < NS; ++j) yi[j] = LG::bcast(mine, j);
+        __syncwarp(LG::mask());                   // the previous values have been consumed
+        if (r < NS) yi[r] = mine;
+        __syncwarp(LG::mask());
     }
     __device__ __forceinline__ void gather(const double* mine, double* full) const {
 #pragma unroll
@@ -222,8 +223,13 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
 
-    Integrator bdf;
+    // per-instance state in shared memory, one record per group (see BdfCtl)
+    struct Shared { typename Integrator::Ctl ctl; double yi[NS]; };
+    __shared__ Shared sh_all[(SB_BLOCK / 32) * (32 / G)];
+    Shared& sh = sh_all[(threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G)];
+    Integrator bdf(sh.ctl);
     Sys sys(a);
+    sys.yi = sh.yi;
     double lam[1], quad[NQL];
     int status;
     bdf.clear_stats();
@@ -243,8 +249,7 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
         bdf.st.nst = ci[2]; bdf.st.nfe = ci[3]; bdf.st.nje = ci[4]; bdf.st.nsetups = ci[5];
         bdf.st.netf = ci[6]; bdf.st.ncfn = ci[7]; bdf.st.nni = ci[8];
     }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+    sys.p = a.params + inst * NP;
     sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
     sys.np = np;
     sys.t = 0.0;

@@ -25,6 +25,9 @@
 #ifndef SB_TAB_PREFETCH_MAX_NS
 #define SB_TAB_PREFETCH_MAX_NS 4
 #endif
+#ifndef SB_GROUP_MIN_BLOCKS
+#define SB_GROUP_MIN_BLOCKS (512 / SB_BLOCK)   /* grouped lanes: 16 warps per SM, <= 128 registers */
+#endif
 #ifndef SB_FLAT_IDLE
 #define SB_FLAT_IDLE 16     /* mean passes a lane may wait per interval before the warp goes flat */
 #endif
@@ -144,7 +147,8 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
     using Sys = FwdSysT<NBLK>;
     using Integrator = Bdf<NS, 0, Sys, NBLK>;
     constexpr int NT = NS * NBLK;
-    Integrator bdf;
+    typename Integrator::Ctl ctl{};
+    Integrator bdf(ctl);
     Sys sys(a);
     double y0[NT];
     if (!valid) inst = 0;
@@ -379,7 +383,8 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
     const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
 
-    Integrator bdf;
+    typename Integrator::Ctl ctl{};
+    Integrator bdf(ctl);
     BwdSys sys(a);
     double lam[NS], quad[ND_];
     int status;
@@ -675,10 +680,10 @@ __device__ __forceinline__ void sb_backward_body(const SbBackwardArgs& a) {
     }
 }
 
-extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, sb::GROUP > 1 ? SB_GROUP_MIN_BLOCKS : SB_MIN_BLOCKS)
 sb_backward(const __grid_constant__ SbBackwardArgs a) { sb_backward_body<false>(a); }
 
-extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, sb::GROUP > 1 ? SB_GROUP_MIN_BLOCKS : SB_MIN_BLOCKS)
 sb_backward_flat(const __grid_constant__ SbBackwardArgs a) { sb_backward_body<true>(a); }
 
 extern "C" __global__ void __launch_bounds__(256)
