@@ -375,6 +375,13 @@ struct BdfCtl {
     int ncf, nef, nefQ, nflag, pend;
     bool jcur, in_step;
 };
+// The matrix rows a lane holds: the saved Jacobian and the Newton matrix I - gamma*J.  With grouped
+// lanes they live in shared memory too (rows padded to an odd number of doubles: conflict-free),
+// where the cross-lane LU can index them at run time and read the pivot row of another lane.
+template <int MSA>
+struct BdfMat {
+    Arr<double, MSA> savedJ, M;
+};
 template <bool REF, class T> struct MemT { using type = T; };
 template <class T> struct MemT<true, T> { using type = T&; };
 
@@ -399,6 +406,7 @@ struct Bdf {
     static constexpr int G = Sys::GROUP;
     static constexpr int MS = (G > 1) ? Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
     static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;        // pivot record
+    static constexpr int MSA = (G > 1) ? (MS | 1) : MS;           // allocated (padded) row length
     __device__ __forceinline__ static double gsum(double x) { if constexpr (G > 1) return Sys::gsum(x); else return x; }
     __device__ __forceinline__ static double gmax(double x) { if constexpr (G > 1) return Sys::gmax(x); else return x; }
     __device__ __forceinline__ static bool gall(bool b) { if constexpr (G > 1) return Sys::gall(b); else return b; }
@@ -448,7 +456,8 @@ struct Bdf {
     Mem<int> q, qprime, qwait, L, qu;
     Mem<bool> jcur;
     // linear solver
-    double savedJ[MS], M[MS];
+    using Mat = BdfMat<MSA>;
+    Mem<Arr<double, MSA>> savedJ, M;
     Mem<Arr<int, PS>> piv;
     // counters
     Mem<int> nst, nstlp, nstlj;
@@ -464,8 +473,8 @@ struct Bdf {
     // rescale / order-change code exists once instead of once per failure branch.
     Mem<int> pend;
 
-    __device__ __forceinline__ explicit Bdf(Ctl& c)
-        : tau(c.tau), l(c.l), tq(c.tq), h(c.h), hprime(c.hprime), hscale(c.hscale), eta(c.eta),
+    __device__ __forceinline__ Bdf(Ctl& c, Mat& mat)
+        : savedJ(mat.savedJ), M(mat.M), tau(c.tau), l(c.l), tq(c.tq), h(c.h), hprime(c.hprime), hscale(c.hscale), eta(c.eta),
           etamax(c.etamax), tn(c.tn), hu(c.hu), rl1(c.rl1), gamma(c.gamma), gammap(c.gammap),
           gamrat(c.gamrat), crate2(c.crate2), delp2(c.delp2), acnrm2(c.acnrm2),
           saved_tq5(c.saved_tq5), q(c.q), qprime(c.qprime), qwait(c.qwait), L(c.L), qu(c.qu),
@@ -893,20 +902,20 @@ struct Bdf {
                           (convfail == FAIL_BAD_J && dgamma < LS_DGMAX) || (convfail == FAIL_OTHER);
         if (jbad) {
             st.nje++; nstlj = nst; jcur = true;
-            sys.jac(ypred, savedJ);
-            if (!gall(all_finite<MS>(savedJ))) return 1;
+            sys.jac(ypred, savedJ.v);
+            if (!gall(all_finite<MS>(savedJ.v))) return 1;
         } else {
             jcur = false;
         }
 #pragma unroll
         for (int k = 0; k < MS; ++k) M[k] = -gamma * savedJ[k];
         if constexpr (G > 1) {
-            Sys::add_identity(M);
-            return Sys::lu_factor(M, piv.v) ? 0 : 1;
+            Sys::add_identity(M.v);
+            return Sys::lu_factor(M.v, piv.v) ? 0 : 1;
         } else {
 #pragma unroll
             for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
-            return lu_factor<NM>(M, piv.v) ? 0 : 1;
+            return lu_factor<NM>(M.v, piv.v) ? 0 : 1;
         }
     }
 
@@ -924,6 +933,8 @@ struct Bdf {
         int retval = 1;
         bool done = !go;
         if (go) sys.set_time(tn);
+        // (rolled: the kernels are instruction-fetch bound and the loop bodies are long)
+#pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
             bool live = !done;
             if (live) {
@@ -947,13 +958,14 @@ struct Bdf {
                 for (int i = 0; i < N; ++i) delta[i] = fma(gamma, f[i], -fma(rl1, zn[1][i], acor[i]));
                 // delta now holds -(rl1*zn1 + acor - gamma*f) = -G
             }
+#pragma unroll 1
             for (int m = 0; m < NLS_MAXCOR; ++m) {
                 if (run) {
                     st.nni++;
 #pragma unroll
                     for (int b = 0; b < NBLK; ++b) {
-                        if constexpr (G > 1) Sys::lu_solve(M, piv.v, delta + b * NM);
-                        else lu_solve<NM>(M, piv.v, delta + b * NM);
+                        if constexpr (G > 1) Sys::lu_solve(M.v, piv.v, delta + b * NM);
+                        else lu_solve<NM>(M.v, piv.v, delta + b * NM);
                     }
                     if (gamrat != 1.0) {
                         const double sc = sb_div(2.0, 1.0 + gamrat);

@@ -45,41 +45,54 @@ struct LaneGroup {
         return r;
     }
 
-    // ---- dense LU across the lanes: lane r < N_ holds row r of the matrix in m[0..N_-1] ---------
-    // Partial pivoting without moving rows: piv[k] is the lane whose row is the k-th pivot row.
-    // After the factorisation a lane pivoted at step s holds the multipliers of steps < s in
-    // m[0..s-1], the RECIPROCAL pivot in m[s] and its U entries in m[s+1..].
-    template <int N_>
+    // ---- dense LU across the lanes ------------------------------------------------------------
+    // Lane r < N_ holds row r of the matrix in SHARED memory, m[0..N_-1]; the rows of the lanes of a
+    // warp follow each other with a stride of STRIDE doubles (odd: conflict-free), so the row of
+    // lane w is at m + (w - r) * STRIDE and every loop below runs over run-time indices (compact
+    // code: this kernel is instruction-fetch bound).  Partial pivoting without moving rows: piv[k]
+    // is the lane whose row is the k-th pivot row.  After the factorisation a lane pivoted at step s
+    // holds the multipliers of steps < s in m[0..s-1], the RECIPROCAL pivot in m[s] and its U
+    // entries in m[s+1..].
+    template <int N_, int STRIDE>
     __device__ __forceinline__ static bool lu_factor(double* m, int* piv) {
         const int r = rank();
+        const unsigned gm = mask();
         bool ok = true;
         bool used = r >= N_;                       // padding lanes hold no row
-        static_for<0, N_>([&](auto K_) {
-            constexpr int k = SB_IDX(K_);
+#pragma unroll 1
+        for (int k = 0; k < N_; ++k) {
+            __syncwarp(gm);                        // the updates of step k - 1 are visible
             double cand = used ? -1.0 : fabs(m[k]);
             int who = r;
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
-                const double oc = __shfl_xor_sync(mask(), cand, o, G);
-                const int ow = __shfl_xor_sync(mask(), who, o, G);
+                const double oc = __shfl_xor_sync(gm, cand, o, G);
+                const int ow = __shfl_xor_sync(gm, who, o, G);
                 const bool take = (oc > cand) || (oc == cand && ow < who);
                 cand = take ? oc : cand;
                 who = take ? ow : who;
             }
             piv[k] = who;
             if (!(cand > 0.0)) ok = false;
-            const double rp = sb_div(1.0, bcast(m[k], who));
+            const double* prow = m + (who - r) * STRIDE;
+            const double rp = sb_div(1.0, prow[k]);
             const bool me = (r == who);
             const bool elim = !used && !me;
             const double mult = m[k] * rp;
-            static_for<k + 1, N_>([&](auto J_) {
-                constexpr int j = SB_IDX(J_);
-                const double pj = bcast(m[j], who);
-                m[j] = elim ? fma(-mult, pj, m[j]) : m[j];
-            });
-            m[k] = elim ? mult : (me ? rp : m[k]);
+            if (elim) {
+                // fixed trip count with literal offsets (the row is in shared memory; the
+                // predicate replaces a loop over j = k + 1 .. N_ - 1)
+#pragma unroll
+                for (int j = 1; j < N_; ++j)
+                    if (j > k) m[j] = fma(-mult, prow[j], m[j]);
+            }
+            __syncwarp(gm);                        // everybody has read the pivot entry
+            if (elim) m[k] = mult;
+            if (me) { m[k] = rp; m[N_] = (double)k; }     // m[N_] (row padding): my pivot step
             used = used || me;
-        });
+        }
+        if (r >= N_) m[N_] = -1.0;
+        __syncwarp(gm);
         return ok;
     }
 
@@ -87,21 +100,21 @@ struct LaneGroup {
     template <int N_>
     __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
         const int r = rank();
-        int mystep = -1;                           // padding lanes: none
-        static_for<0, N_>([&](auto K_) { constexpr int k = SB_IDX(K_); mystep = (piv[k] == r) ? k : mystep; });
+        const unsigned gm = mask();
+        const int mystep = (int)m[N_];             // the step this lane's row was the pivot row (-1: none)
         double v = b[0];
-        static_for<0, N_>([&](auto K_) {           // L y = P b
-            constexpr int k = SB_IDX(K_);
-            const double vk = bcast(v, piv[k]);
+#pragma unroll
+        for (int k = 0; k < N_; ++k) {             // L y = P b
+            const double vk = __shfl_sync(gm, v, piv[k], G);
             v = (mystep > k) ? fma(-m[k], vk, v) : v;
-        });
+        }
         double x = 0.0;
-        static_for<0, N_>([&](auto K_) {           // U x = y
-            constexpr int k = N_ - 1 - SB_IDX(K_);
-            const double xk = bcast(v * m[k], piv[k]);
+#pragma unroll
+        for (int k = N_ - 1; k >= 0; --k) {        // U x = y
+            const double xk = __shfl_sync(gm, v * m[k], piv[k], G);
             v = (mystep >= 0 && mystep < k) ? fma(-m[k], xk, v) : v;
             x = (r == k) ? xk : x;
-        });
+        }
         b[0] = x;
     }
 };
@@ -124,11 +137,14 @@ struct BwdSysG {
     __device__ __forceinline__ static double gsum(double x) { return LG::sum(x); }
     __device__ __forceinline__ static double gmax(double x) { return LG::max(x); }
     __device__ __forceinline__ static bool gall(bool b) { return LG::all(b); }
+    static constexpr int ROW = NS | 1;             // allocated row length (Bdf::MSA)
     __device__ __forceinline__ static void add_identity(double* m) {
         const int r = LG::rank();
-        static_for<0, NS>([&](auto J_) { constexpr int j = SB_IDX(J_); m[j] += (r == j) ? 1.0 : 0.0; });
+        if (r < NS) m[r] += 1.0;
     }
-    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) { return LG::template lu_factor<NS>(m, piv); }
+    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) {
+        return LG::template lu_factor<NS, 2 * ROW + 1>(m, piv);
+    }
     __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
         LG::template lu_solve<NS>(m, piv, b);
     }
@@ -139,6 +155,7 @@ struct BwdSysG {
     int idx;               // current interval (CVODES' ilast)
     double t;
     double* yi;            // forward solution interpolated at t: the group's [NS] shared-memory slot
+    double* lamv;          // the vector an evaluation is made at, all components: another [NS] slot
 
     // as BwdSys::set_time; the lanes of a group share t and idx, read the knots together (one
     // broadcast load) and one column of the divided differences each (one 8*NS-byte segment per
@@ -176,15 +193,17 @@ struct BwdSysG {
         if (r < NS) yi[r] = mine;
         __syncwarp(LG::mask());
     }
-    __device__ __forceinline__ void gather(const double* mine, double* full) const {
-#pragma unroll
-        for (int j = 0; j < NS; ++j) full[j] = LG::bcast(mine[0], j);
+    // every lane contributes its component; the generated functions then read what they need
+    __device__ __forceinline__ void gather(const double* mine) const {
+        __syncwarp(LG::mask());                   // the previous contents have been consumed
+        if (LG::rank() < NS) lamv[LG::rank()] = mine[0];
+        __syncwarp(LG::mask());
     }
     // every lane evaluates the whole (cheap) function and keeps its own component
     __device__ __forceinline__ void rhs(const double* lam_mine, double* out_mine) const {
-        double lam[NS], out[NS];
-        gather(lam_mine, lam);
-        sb_adj_rhs(t, yi, lam, p, out);
+        double out[NS];
+        gather(lam_mine);
+        sb_adj_rhs(t, yi, lamv, p, out);
         out_mine[0] = LG::template pick<NS>(out, LG::rank());
     }
     __device__ __forceinline__ void jac(const double*, double* Jrow) const {
@@ -197,11 +216,11 @@ struct BwdSysG {
         });
     }
     __device__ __forceinline__ void quad(const double* lam_mine, double* out_mine) const {
-        double lam[NS], out[ND_];
-        gather(lam_mine, lam);
+        double out[ND_];
+        gather(lam_mine);
 #pragma unroll
         for (int i = 0; i < ND_; ++i) out[i] = 0.0;
-        sb_quad_rhs(t, yi, lam, p, out);
+        sb_quad_rhs(t, yi, lamv, p, out);
 #pragma unroll
         for (int c = 0; c < NQL; ++c) out_mine[c] = LG::template pick<ND_>(out, LG::rank() + G * c);
     }
@@ -224,12 +243,17 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     const int np = a.hist_n[inst];
 
     // per-instance state in shared memory, one record per group (see BdfCtl)
-    struct Shared { typename Integrator::Ctl ctl; double yi[NS]; };
+    struct Shared { typename Integrator::Ctl ctl; double yi[NS]; double lamv[NS]; };
     __shared__ Shared sh_all[(SB_BLOCK / 32) * (32 / G)];
     Shared& sh = sh_all[(threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G)];
-    Integrator bdf(sh.ctl);
+    // per-lane matrix rows, also in shared memory; consecutive lanes 2*ROW + 1 doubles apart
+    struct Rows { typename Integrator::Mat mat; double pad; };
+    static_assert(sizeof(Rows) == (2 * Sys::ROW + 1) * sizeof(double), "row stride");
+    __shared__ Rows rows_all[SB_BLOCK];
+    Integrator bdf(sh.ctl, rows_all[threadIdx.x].mat);
     Sys sys(a);
     sys.yi = sh.yi;
+    sys.lamv = sh.lamv;
     double lam[1], quad[NQL];
     int status;
     bdf.clear_stats();

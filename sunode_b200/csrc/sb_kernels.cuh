@@ -148,7 +148,8 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
     using Integrator = Bdf<NS, 0, Sys, NBLK>;
     constexpr int NT = NS * NBLK;
     typename Integrator::Ctl ctl{};
-    Integrator bdf(ctl);
+    typename Integrator::Mat mat{};
+    Integrator bdf(ctl, mat);
     Sys sys(a);
     double y0[NT];
     if (!valid) inst = 0;
@@ -384,7 +385,8 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
     const int np = a.hist_n[inst];
 
     typename Integrator::Ctl ctl{};
-    Integrator bdf(ctl);
+    typename Integrator::Mat mat{};
+    Integrator bdf(ctl, mat);
     BwdSys sys(a);
     double lam[NS], quad[ND_];
     int status;
