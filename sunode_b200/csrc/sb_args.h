@@ -12,8 +12,10 @@
 /* Lanes of a warp that integrate one instance together (sb_group.cuh): one for small systems, a
  * power-of-two group with one state component per lane from SB_GROUP_MIN_NS states on; beyond 32
  * states one lane per instance again (loop-based LU in local memory). */
+#ifndef SB_GROUP_MIN_NS
 #define SB_GROUP_MIN_NS 5
-#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 8 ? 8 : (ns) <= 16 ? 16 : (ns) <= 32 ? 32 : 1)
+#endif
+#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 2 ? 2 : (ns) <= 4 ? 4 : (ns) <= 8 ? 8 : (ns) <= 16 ? 16 : (ns) <= 32 ? 32 : 1)
 
 #define SB_HIST_STRIDE(ns) ((ns) + 2)
 #define SB_TAB_STRIDE(ns) (10 + 6 * (ns))

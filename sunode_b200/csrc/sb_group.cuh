@@ -15,6 +15,8 @@
 
 namespace sb {
 
+#define SB_GROUP_SPLIT (-1006)     /* SB_GROUP_CHECK builds: the lanes of a group were found separated */
+
 template <int G>
 struct LaneGroup {
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
@@ -36,6 +38,28 @@ struct LaneGroup {
         return x;
     }
     __device__ __forceinline__ static bool all(bool b) { return __all_sync(mask(), b) != 0; }
+    // The per-instance state in shared memory is updated by every lane of the group with the same
+    // value in the same instruction; updates like `nst++` or `tn += h` are only correct while the
+    // lanes of a group execute TOGETHER.  Group-uniform branches keep them together; after every
+    // lane-dependent branch (and wherever the lanes may have been separated before the group code
+    // starts) they are joined again here.  -DSB_GROUP_CHECK turns the assumption into a test: a
+    // group that is found split reports SB_GROUP_SPLIT through the instance status.
+    __device__ __forceinline__ static bool converge() {
+        __syncwarp(mask());
+#ifdef SB_GROUP_CHECK
+        return (__activemask() & mask()) == mask();
+#else
+        return true;
+#endif
+    }
+    // SB_GROUP_CHECK: are the lanes of the group together right now (no joining)?
+    __device__ __forceinline__ static bool together() {
+#ifdef SB_GROUP_CHECK
+        return (__activemask() & mask()) == mask();
+#else
+        return true;
+#endif
+    }
 
     // register array element `rank` (0 for lanes past the end) without dynamic indexing
     template <int N_>
@@ -277,18 +301,21 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
     sys.np = np;
     sys.t = 0.0;
+    bool joined = LG::converge();                       // (the carry loads above are lane-dependent)
     bdf.reinit(a.t_start, lam, quad);
 
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
     for (int k = k_begin; k < k_end; ++k) {
         const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
         const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
+        joined = LG::converge() && joined;
         if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
             if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
             const bool live = valid && status == SB_SUCCESS;
             if (live) {
                 bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
                 status = bdf.first_call(sys, t_lower);
+                joined = LG::together() && joined;      // (the restart ran with the group together)
             }
             int nloc = 0;
             bool reached = false;
@@ -301,6 +328,10 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
                 }
                 const unsigned mask = sb_ballot(work);
                 if (mask == 0u) break;
+                // (the pass that just ended must have left the group together: its shared-memory
+                // updates were made after the previous join)
+                joined = LG::together() && joined;
+                joined = LG::converge() && joined;
                 if (work) {
                     const int rr = bdf.attempt(sys, mask);
                     if (rr == SB_SUCCESS) {
@@ -332,6 +363,8 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
             }
         }
     }
+    joined = LG::converge() && joined;
+    if (!joined && status == SB_SUCCESS) status = SB_GROUP_SPLIT;    // SB_GROUP_CHECK builds only
     if (!valid) return;
     if (!last) {
         double* cd = a.carry_d + (size_t)inst * (NS + ND_);

@@ -642,23 +642,32 @@ __device__ __forceinline__ void sb_backward_body(const SbBackwardArgs& a) {
         int u = 0;
         if (lane == 0) u = atomicAdd(a.queue, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
+        __syncwarp(0xffffffffu);                   // lane 0 re-joins (grouped lanes must run together)
         if (u >= total) break;
         const int seg = u / a.n_groups, grp = u - seg * a.n_groups;
         int timed_out = 0;
         if (seg > 0) {
-            if (lane == 0) {
-                volatile int* done = a.seg_done;
-                unsigned long long t_begin = 0, t_now = 0;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-                while (done[grp] < seg) {
-                    __nanosleep(200);
+            // Wait for the predecessor unit.  Lane 0 looks, all lanes follow its verdict: the loop
+            // is warp-uniform on purpose -- a spin loop run by lane 0 alone left that lane
+            // separated from the rest of its warp long after the loop (observed with grouped
+            // lanes, whose shared per-instance state needs the lanes of a group to run together).
+            unsigned long long t_begin = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+            for (;;) {
+                int verdict = 0;                   // 0 not yet, 1 ready, 2 timed out
+                if (lane == 0) {
+                    unsigned long long t_now = 0;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                    const volatile int* done = a.seg_done;
                     // safety net only (a predecessor unit is always running or done): 60 s
-                    if (t_now - t_begin > 60000000000ULL) { timed_out = 1; break; }
+                    verdict = (done[grp] >= seg) ? 1 : ((t_now - t_begin > 60000000000ULL) ? 2 : 0);
                 }
+                verdict = __shfl_sync(0xffffffffu, verdict, 0);
+                if (verdict != 0) { timed_out = verdict == 2; break; }
+                __nanosleep(200);
             }
-            timed_out = __shfl_sync(0xffffffffu, timed_out, 0);
             __threadfence();
+            __syncwarp(0xffffffffu);
         }
         // a.lanes instances per warp: one per lane, or one per group of sb::GROUP lanes
         const int slot = lane / sb::GROUP;

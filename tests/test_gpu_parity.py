@@ -259,3 +259,70 @@ def test_segmented_work_queue_is_transparent(monkeypatch):
             else:
                 for a, b in zip(ref, out + (sb,)):
                     np.testing.assert_array_equal(a, b)
+
+
+def test_interval_schedule_is_transparent(monkeypatch):
+    """sb_backward (lanes of a warp restart together) and sb_backward_flat (every lane walks its
+    intervals on its own) perform the same per-instance computation: bit-identical outputs and
+    counters, whichever the device-side rule or SUNODE_B200_FLAT picks (stiff and non-stiff)."""
+    for name, B in (('lv_adj', 100), ('robertson_adj', 70)):
+        w = examples.workloads()[name]
+        prob = w.make_problem()
+        solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=w.history_capacity)
+        y0, theta = w.draws(B)
+        grads = np.random.default_rng(4).standard_normal((B, len(w.tvals), prob.n_states))
+        ref = None
+        for flat in (None, '0', '1'):
+            if flat is None:
+                monkeypatch.delenv('SUNODE_B200_FLAT', raising=False)
+            else:
+                monkeypatch.setenv('SUNODE_B200_FLAT', flat)
+            sb = np.zeros((B, 8), np.int32)
+            out = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_bwd=sb) + (sb,)
+            assert (out[3] == 0).all()
+            if ref is None:
+                ref = out
+            else:
+                for a, b in zip(ref, out):
+                    np.testing.assert_array_equal(a, b)
+
+
+def test_lane_groups_match_one_lane_per_instance(monkeypatch):
+    """SEIR (8 states) runs with 8 lanes per instance (sb_group.cuh: one state component per lane,
+    LU across the lanes with shuffles, norms as butterfly sums).  Same algorithm as the
+    one-lane-per-instance build (-DSB_NO_GROUP), different summation order in the norms: the step
+    sequences agree but for rounding-level decision flips and the results to 1e-9; segmentation
+    is bit-transparent in group mode too; batch sizes that leave groups / warps partly empty."""
+    w = examples.workloads()['seir_adj']
+    prob = w.make_problem()
+    rng = np.random.default_rng(8)
+    for B in (3, 4 * 37 + 1):
+        y0, theta = w.draws(B)
+        grads = rng.standard_normal((B, len(w.tvals), prob.n_states))
+        outs = {}
+        for defines in ('', 'SB_NO_GROUP', 'SB_GROUP_CHECK'):
+            monkeypatch.setenv('SUNODE_B200_DEFINES', defines)
+            solver = AdjointSolver(w.make_problem(), abstol=1e-8, reltol=1e-8, history_capacity=512)
+            sb = np.zeros((B, 8), np.int32)
+            out = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_bwd=sb) + (sb,)
+            assert (out[3] == 0).all()
+            outs[defines] = out
+            if defines in ('', 'SB_GROUP_CHECK'):
+                for seg in ('1', '7', '51'):
+                    monkeypatch.setenv('SUNODE_B200_SEGMENTS', seg)
+                    sb2 = np.zeros((B, 8), np.int32)
+                    out2 = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_bwd=sb2) + (sb2,)
+                    for a, b in zip(out, out2):
+                        np.testing.assert_array_equal(a, b)
+                monkeypatch.delenv('SUNODE_B200_SEGMENTS')
+        # the build that verifies, on the device, that the lanes of a group ran together wherever
+        # they update their shared per-instance state (status -1006 otherwise)
+        for a, b in zip(outs[''], outs['SB_GROUP_CHECK']):
+            np.testing.assert_array_equal(a, b)
+        g, t = outs[''], outs['SB_NO_GROUP']
+        np.testing.assert_array_equal(g[0], t[0])                      # forward: same kernel
+        scale = np.abs(t[1]).max(axis=0)
+        assert np.max(np.abs(g[1] - t[1]) / scale) <= 1e-9
+        assert np.max(np.abs(g[2] - t[2]) / np.abs(t[2]).max(axis=0)) <= 1e-9
+        if B > 100:
+            assert (g[4][:, 0] == t[4][:, 0]).mean() >= 0.9           # backward step counts
