@@ -283,7 +283,11 @@ struct BwdSys {
     // CVodeB stops the backward integrator at the start of the checkpoint interval, i.e. the
     // forward problem's initial time; it steps past each t_lower and interpolates back
     __device__ __forceinline__ double tstop() const { return a.t_end; }
+#ifdef SB_PARAMS_IN_MEMORY
+    const double* p;       // this instance's parameters, read from (L1-cached) global memory
+#else
     double p[NP_];
+#endif
     const double* tab;     // this instance's table base
     int np;                // stored points; intervals are 1 .. np-1
     int idx;               // current interval (CVODES' ilast)
@@ -410,8 +414,12 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
         bdf.st.netf = ci[6]; bdf.st.ncfn = ci[7]; bdf.st.nni = ci[8];
     }
 
+#ifdef SB_PARAMS_IN_MEMORY
+    sys.p = a.params + inst * NP;
+#else
 #pragma unroll
     for (int i = 0; i < NP; ++i) sys.p[i] = a.params[inst * NP + i];
+#endif
     sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
     sys.np = np;
     sys.t = 0.0;
@@ -651,16 +659,20 @@ __device__ __forceinline__ void sb_backward_body(const SbBackwardArgs& a) {
             // is warp-uniform on purpose -- a spin loop run by lane 0 alone left that lane
             // separated from the rest of its warp long after the loop (observed with grouped
             // lanes, whose shared per-instance state needs the lanes of a group to run together).
-            unsigned long long t_begin = 0;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+            unsigned long long t_begin = 0;        // (lane 0) set when the first look finds the unit not ready
             for (;;) {
                 int verdict = 0;                   // 0 not yet, 1 ready, 2 timed out
                 if (lane == 0) {
-                    unsigned long long t_now = 0;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
                     const volatile int* done = a.seg_done;
-                    // safety net only (a predecessor unit is always running or done): 60 s
-                    verdict = (done[grp] >= seg) ? 1 : ((t_now - t_begin > 60000000000ULL) ? 2 : 0);
+                    if (done[grp] >= seg) {
+                        verdict = 1;
+                    } else {
+                        // safety net only (a predecessor unit is always running or done): 60 s
+                        unsigned long long t_now = 0;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                        if (t_begin == 0) t_begin = t_now;
+                        else if (t_now - t_begin > 60000000000ULL) verdict = 2;
+                    }
                 }
                 verdict = __shfl_sync(0xffffffffu, verdict, 0);
                 if (verdict != 0) { timed_out = verdict == 2; break; }
