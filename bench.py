@@ -376,8 +376,15 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get('%s:%d:%s' % (w.name, B, 'sb_backward' if w.adjoint else 'sb_forward'))
+    from sunode_b200._engine import lanes_per_instance, FLAT_FWD_STEPS_PER_TVAL
+    group = lanes_per_instance(n_s)
+    # which build of the backward kernel did the work (the device-side rule of sb_api.cpp)
+    flat = w.adjoint and group == 1 and mean_fwd_steps * (1 - n_fail / max(B, 1)) > FLAT_FWD_STEPS_PER_TVAL * n_t
     roofline = {
-        'bound': 'hbm', 'kernel': 'sb_backward' if w.adjoint else 'sb_forward',
+        'bound': 'hbm', 'kernel': ('sb_backward_flat' if flat else 'sb_backward') if w.adjoint else 'sb_forward',
+        'lanes_per_instance': {'forward': 1, 'backward': group if w.adjoint else None},
+        'backward_schedule': None if not w.adjoint else (
+            'every lane walks its intervals on its own' if flat else 'lanes of a warp restart together'),
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
         'traffic': traffic, 'traffic_source': 'ncu --set full capture, profiles/ncu_traffic.json' if traffic else None,
         'peak_source': peak_src,

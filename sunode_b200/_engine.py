@@ -297,6 +297,20 @@ class Engine:
         return {k: v.value for k, v in zip(keys, vals)}
 
 
+def lanes_per_instance(n_states: int) -> int:
+    """Lanes of a warp that integrate one instance in the backward kernels: ``SB_GROUP_SIZE`` of
+    ``csrc/sb_args.h`` (one lane up to 4 states, then a power-of-two group with one state
+    component per lane, see ``csrc/sb_group.cuh``)."""
+    if 'SB_NO_GROUP' in os.environ.get('SUNODE_B200_DEFINES', ''):
+        return 1
+    if n_states < 5 or n_states > 32:
+        return 1
+    return 8 if n_states <= 8 else 16 if n_states <= 16 else 32
+
+
+FLAT_FWD_STEPS_PER_TVAL = 8     # SB_FLAT_FWD_STEPS_PER_TVAL of csrc/sb_api.cpp
+
+
 class PinnedBuffer:
     """Page-locked host array (``sb_host_alloc``) for asynchronous staging."""
 
