@@ -407,11 +407,12 @@ struct Bdf {
     static constexpr int MS = (G > 1) ? Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
     static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;        // pivot record
     static constexpr int MSA = (G > 1) ? (MS | 1) : MS;           // allocated (padded) row length
-    __device__ __forceinline__ static double gsum(double x) { if constexpr (G > 1) return Sys::gsum(x); else return x; }
-    __device__ __forceinline__ static double gmax(double x) { if constexpr (G > 1) return Sys::gmax(x); else return x; }
-    __device__ __forceinline__ static bool gall(bool b) { if constexpr (G > 1) return Sys::gall(b); else return b; }
+    typename Sys::GroupIds gid;                  // grouped lanes: lane mask + rank (empty otherwise)
+    __device__ __forceinline__ double gsum(double x) const { if constexpr (G > 1) return Sys::gsum(x, gid); else return x; }
+    __device__ __forceinline__ double gmax(double x) const { if constexpr (G > 1) return Sys::gmax(x, gid); else return x; }
+    __device__ __forceinline__ bool gall(bool b) const { if constexpr (G > 1) return Sys::gall(b, gid); else return b; }
     // mean of the squared weighted components of a state-sized block / of a quadrature vector
-    __device__ __forceinline__ static double ms_y(const double* v, const double* w) {
+    __device__ __forceinline__ double ms_y(const double* v, const double* w) const {
         if constexpr (G > 1) { const double x = v[0] * w[0]; return gsum(x * x) * (1.0 / Sys::NS_FULL); }
         else return wms<NM>(v, w);
     }
@@ -423,8 +424,8 @@ struct Bdf {
             return gsum(s) * (1.0 / Sys::NQ_FULL);
         } else return wms<NQ_>(v, ewtQ);
     }
-    __device__ __forceinline__ static bool finite_y(const double* v) { return gall(all_finite<N>(v)); }
-    __device__ __forceinline__ static bool finite_q(const double* v) { return gall(all_finite<NQ_>(v)); }
+    __device__ __forceinline__ bool finite_y(const double* v) const { return gall(all_finite<N>(v)); }
+    __device__ __forceinline__ bool finite_q(const double* v) const { return gall(all_finite<NQ_>(v)); }
 
     // max over blocks of the weighted RMS norm (one block: the plain WRMS norm)
     __device__ __forceinline__ double norm(const double* v) const { return sb_sqrt(norm2(v)); }
@@ -910,8 +911,8 @@ struct Bdf {
 #pragma unroll
         for (int k = 0; k < MS; ++k) M[k] = -gamma * savedJ[k];
         if constexpr (G > 1) {
-            Sys::add_identity(M.v);
-            return Sys::lu_factor(M.v, piv.v) ? 0 : 1;
+            sys.add_identity(M.v);
+            return sys.lu_factor(M.v, piv.v) ? 0 : 1;
         } else {
 #pragma unroll
             for (int i = 0; i < NM; ++i) M[i + NM * i] += 1.0;
@@ -964,7 +965,7 @@ struct Bdf {
                     st.nni++;
 #pragma unroll
                     for (int b = 0; b < NBLK; ++b) {
-                        if constexpr (G > 1) Sys::lu_solve(M.v, piv.v, delta + b * NM);
+                        if constexpr (G > 1) sys.lu_solve(M.v, piv.v, delta + b * NM);
                         else lu_solve<NM>(M.v, piv.v, delta + b * NM);
                     }
                     if (gamrat != 1.0) {

@@ -25,38 +25,47 @@ struct LaneGroup {
         if constexpr (G == 32) return 0xffffffffu;
         else return ((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
     }
-    __device__ __forceinline__ static double bcast(double x, int src) { return __shfl_sync(mask(), x, src, G); }
-    __device__ __forceinline__ static double sum(double x) {
+    // The group's lane mask and the lane's rank are computed once and kept in registers (`Ids`,
+    // laundered through an asm so that the compiler does not re-derive them from %tid before
+    // every shuffle: ncu showed 800 S2R/shift sequences, each in front of a shuffle).
+    struct Ids { unsigned gm; int r; };
+    __device__ __forceinline__ static Ids ids() {
+        Ids v;
+        asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(v.gm), "=r"(v.r) : "r"(mask()), "r"(rank()));
+        return v;
+    }
+    __device__ __forceinline__ static double sum(double x, unsigned gm) {
         // xor butterfly: every lane ends with the bitwise identical sum
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask(), x, o, G);
+        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gm, x, o, G);
         return x;
     }
-    __device__ __forceinline__ static double max(double x) {
+    __device__ __forceinline__ static double max(double x, unsigned gm) {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(mask(), x, o, G));
+        for (int o = G / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(gm, x, o, G));
         return x;
     }
-    __device__ __forceinline__ static bool all(bool b) { return __all_sync(mask(), b) != 0; }
+    __device__ __forceinline__ static bool all(bool b, unsigned gm) { return __all_sync(gm, b) != 0; }
     // The per-instance state in shared memory is updated by every lane of the group with the same
     // value in the same instruction; updates like `nst++` or `tn += h` are only correct while the
     // lanes of a group execute TOGETHER.  Group-uniform branches keep them together; after every
     // lane-dependent branch (and wherever the lanes may have been separated before the group code
     // starts) they are joined again here.  -DSB_GROUP_CHECK turns the assumption into a test: a
     // group that is found split reports SB_GROUP_SPLIT through the instance status.
-    __device__ __forceinline__ static bool converge() {
-        __syncwarp(mask());
+    __device__ __forceinline__ static bool converge(unsigned gm) {
+        __syncwarp(gm);
 #ifdef SB_GROUP_CHECK
-        return (__activemask() & mask()) == mask();
+        return (__activemask() & gm) == gm;
 #else
         return true;
 #endif
     }
     // SB_GROUP_CHECK: are the lanes of the group together right now (no joining)?
-    __device__ __forceinline__ static bool together() {
+    __device__ __forceinline__ static bool together(unsigned gm) {
 #ifdef SB_GROUP_CHECK
-        return (__activemask() & mask()) == mask();
+        return (__activemask() & gm) == gm;
 #else
+        (void)gm;
         return true;
 #endif
     }
@@ -78,9 +87,9 @@ struct LaneGroup {
     // holds the multipliers of steps < s in m[0..s-1], the RECIPROCAL pivot in m[s] and its U
     // entries in m[s+1..].
     template <int N_, int STRIDE>
-    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) {
-        const int r = rank();
-        const unsigned gm = mask();
+    __device__ __forceinline__ static bool lu_factor(double* m, int* piv, Ids id) {
+        const int r = id.r;
+        const unsigned gm = id.gm;
         bool ok = true;
         bool used = r >= N_;                       // padding lanes hold no row
 #pragma unroll 1
@@ -122,9 +131,9 @@ struct LaneGroup {
 
     // b[0]: entry `rank` of the right-hand side on entry, of the solution on return
     template <int N_>
-    __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
-        const int r = rank();
-        const unsigned gm = mask();
+    __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b, Ids id) {
+        const int r = id.r;
+        const unsigned gm = id.gm;
         const int mystep = (int)m[N_];             // the step this lane's row was the pivot row (-1: none)
         double v = b[0];
 #pragma unroll
@@ -152,25 +161,26 @@ struct BwdSysG {
     static constexpr int NQL = (ND + G - 1) / G > 0 ? (ND + G - 1) / G : 1;   // quadrature components per lane
     static_assert(NS <= G, "one state component per lane");
     const SbBackwardArgs& a;
-    __device__ __forceinline__ explicit BwdSysG(const SbBackwardArgs& a_) : a(a_) {}
+    using GroupIds = typename LG::Ids;
+    GroupIds id;           // group mask and rank of this lane
+    __device__ __forceinline__ explicit BwdSysG(const SbBackwardArgs& a_) : a(a_), id(LG::ids()) {}
     __device__ __forceinline__ double rtol() const { return a.rtol; }
     __device__ __forceinline__ double atol(int) const { return a.atol; }
     __device__ __forceinline__ double rtolQ() const { return a.rtol_q; }
     __device__ __forceinline__ double atolQ() const { return a.atol_q; }
     __device__ __forceinline__ double tstop() const { return a.t_end; }
-    __device__ __forceinline__ static double gsum(double x) { return LG::sum(x); }
-    __device__ __forceinline__ static double gmax(double x) { return LG::max(x); }
-    __device__ __forceinline__ static bool gall(bool b) { return LG::all(b); }
+    __device__ __forceinline__ static double gsum(double x, GroupIds g) { return LG::sum(x, g.gm); }
+    __device__ __forceinline__ static double gmax(double x, GroupIds g) { return LG::max(x, g.gm); }
+    __device__ __forceinline__ static bool gall(bool b, GroupIds g) { return LG::all(b, g.gm); }
     static constexpr int ROW = NS | 1;             // allocated row length (Bdf::MSA)
-    __device__ __forceinline__ static void add_identity(double* m) {
-        const int r = LG::rank();
-        if (r < NS) m[r] += 1.0;
+    __device__ __forceinline__ void add_identity(double* m) const {
+        if (id.r < NS) m[id.r] += 1.0;
     }
-    __device__ __forceinline__ static bool lu_factor(double* m, int* piv) {
-        return LG::template lu_factor<NS, 2 * ROW + 1>(m, piv);
+    __device__ __forceinline__ bool lu_factor(double* m, int* piv) const {
+        return LG::template lu_factor<NS, 2 * ROW + 1>(m, piv, id);
     }
-    __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b) {
-        LG::template lu_solve<NS>(m, piv, b);
+    __device__ __forceinline__ void lu_solve(const double* m, const int* piv, double* b) const {
+        LG::template lu_solve<NS>(m, piv, b, id);
     }
 
     const double* p;       // this instance's parameters (global memory, read where needed)
@@ -186,7 +196,7 @@ struct BwdSysG {
     // row and group), then exchange the interpolated components
     __device__ __forceinline__ void set_time(double t_) {
         t = t_;
-        const int r = LG::rank();
+        const int r = id.r;
         const int col = r < NS ? r : 0;
         const double* e = tab + (size_t)idx * TAB_STRIDE;
         double lo, hi, inv_delt, T[SB_QMAX], Y[SB_LMAX];
@@ -213,27 +223,27 @@ struct BwdSysG {
             c = (i < order) ? c * ((t - T[i]) * inv_delt) : 0.0;
             mine = fma(c, Y[i + 1], mine);
         }
-        __syncwarp(LG::mask());                   // the previous values have been consumed
+        __syncwarp(id.gm);                        // the previous values have been consumed
         if (r < NS) yi[r] = mine;
-        __syncwarp(LG::mask());
+        __syncwarp(id.gm);
     }
     // every lane contributes its component; the generated functions then read what they need
     __device__ __forceinline__ void gather(const double* mine) const {
-        __syncwarp(LG::mask());                   // the previous contents have been consumed
-        if (LG::rank() < NS) lamv[LG::rank()] = mine[0];
-        __syncwarp(LG::mask());
+        __syncwarp(id.gm);                        // the previous contents have been consumed
+        if (id.r < NS) lamv[id.r] = mine[0];
+        __syncwarp(id.gm);
     }
     // every lane evaluates the whole (cheap) function and keeps its own component
     __device__ __forceinline__ void rhs(const double* lam_mine, double* out_mine) const {
         double out[NS];
         gather(lam_mine);
         sb_adj_rhs(t, yi, lamv, p, out);
-        out_mine[0] = LG::template pick<NS>(out, LG::rank());
+        out_mine[0] = LG::template pick<NS>(out, id.r);
     }
     __device__ __forceinline__ void jac(const double*, double* Jrow) const {
         double J[NS * NS];
         sb_adj_jac(t, yi, p, J);
-        const int r = LG::rank();
+        const int r = id.r;
         static_for<0, NS>([&](auto J_) {
             constexpr int j = SB_IDX(J_);
             Jrow[j] = LG::template pick<NS>(J + NS * j, r);     // column-major: J[r + NS*j]
@@ -246,7 +256,7 @@ struct BwdSysG {
         for (int i = 0; i < ND_; ++i) out[i] = 0.0;
         sb_quad_rhs(t, yi, lamv, p, out);
 #pragma unroll
-        for (int c = 0; c < NQL; ++c) out_mine[c] = LG::template pick<ND_>(out, LG::rank() + G * c);
+        for (int c = 0; c < NQL; ++c) out_mine[c] = LG::template pick<ND_>(out, id.r + G * c);
     }
 };
 
@@ -261,7 +271,9 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     constexpr int NQL = Sys::NQL;
     using Integrator = Bdf<1, (ND > 0 ? NQL : 0), Sys>;
     if (!valid) inst = 0;
-    const int r = LG::rank();
+    Sys sys(a);
+    const int r = sys.id.r;
+    const unsigned gm = sys.id.gm;
     const bool has_y = r < NS;
     const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
@@ -275,7 +287,7 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     static_assert(sizeof(Rows) == (2 * Sys::ROW + 1) * sizeof(double), "row stride");
     __shared__ Rows rows_all[SB_BLOCK];
     Integrator bdf(sh.ctl, rows_all[threadIdx.x].mat);
-    Sys sys(a);
+    bdf.gid = sys.id;
     sys.yi = sh.yi;
     sys.lamv = sh.lamv;
     double lam[1], quad[NQL];
@@ -301,21 +313,21 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     sys.tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
     sys.np = np;
     sys.t = 0.0;
-    bool joined = LG::converge();                       // (the carry loads above are lane-dependent)
+    bool joined = LG::converge(gm);                       // (the carry loads above are lane-dependent)
     bdf.reinit(a.t_start, lam, quad);
 
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
     for (int k = k_begin; k < k_end; ++k) {
         const double t_upper = (k == 0) ? a.t_start : a.tvals[a.n_t - k];
         const double t_lower = (k == a.n_t) ? a.t_end : a.tvals[a.n_t - 1 - k];
-        joined = LG::converge() && joined;
+        joined = LG::converge(gm) && joined;
         if (t_lower < t_upper) {                        // warp-uniform: tvals are shared
             if (valid && status == SB_SUCCESS && np < 2) status = SB_ILL_INPUT;
             const bool live = valid && status == SB_SUCCESS;
             if (live) {
                 bdf.reinit(t_upper, lam, quad);         // CVodeReInitB + CVodeQuadReInitB
                 status = bdf.first_call(sys, t_lower);
-                joined = LG::together() && joined;      // (the restart ran with the group together)
+                joined = LG::together(gm) && joined;      // (the restart ran with the group together)
             }
             int nloc = 0;
             bool reached = false;
@@ -330,8 +342,8 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
                 if (mask == 0u) break;
                 // (the pass that just ended must have left the group together: its shared-memory
                 // updates were made after the previous join)
-                joined = LG::together() && joined;
-                joined = LG::converge() && joined;
+                joined = LG::together(gm) && joined;
+                joined = LG::converge(gm) && joined;
                 if (work) {
                     const int rr = bdf.attempt(sys, mask);
                     if (rr == SB_SUCCESS) {
@@ -363,7 +375,7 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
             }
         }
     }
-    joined = LG::converge() && joined;
+    joined = LG::converge(gm) && joined;
     if (!joined && status == SB_SUCCESS) status = SB_GROUP_SPLIT;    // SB_GROUP_CHECK builds only
     if (!valid) return;
     if (!last) {

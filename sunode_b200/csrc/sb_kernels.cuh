@@ -57,6 +57,7 @@ template <int NBLK>
 struct FwdSysT {
     static constexpr bool TSTOP = false;
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = 1;
+    struct GroupIds {};
     const SbForwardArgs& a;
     double p[NP_];
     double t;
@@ -147,8 +148,13 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
     using Sys = FwdSysT<NBLK>;
     using Integrator = Bdf<NS, 0, Sys, NBLK>;
     constexpr int NT = NS * NBLK;
+#ifdef SB_CTL_ZERO_INIT
     typename Integrator::Ctl ctl{};
     typename Integrator::Mat mat{};
+#else
+    typename Integrator::Ctl ctl;      // every field is set by reinit() / the first setup before use
+    typename Integrator::Mat mat;
+#endif
     Integrator bdf(ctl, mat);
     Sys sys(a);
     double y0[NT];
@@ -274,6 +280,7 @@ __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long lo
 struct BwdSys {
     static constexpr bool TSTOP = true;
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = ND_;
+    struct GroupIds {};
     const SbBackwardArgs& a;
     __device__ __forceinline__ explicit BwdSys(const SbBackwardArgs& a_) : a(a_) {}
     __device__ __forceinline__ double rtol() const { return a.rtol; }
@@ -388,8 +395,13 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
     const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
 
+#ifdef SB_CTL_ZERO_INIT
     typename Integrator::Ctl ctl{};
     typename Integrator::Mat mat{};
+#else
+    typename Integrator::Ctl ctl;      // every field is set by reinit() / the first setup before use
+    typename Integrator::Mat mat;
+#endif
     Integrator bdf(ctl, mat);
     BwdSys sys(a);
     double lam[NS], quad[ND_];
