@@ -383,6 +383,11 @@ struct BdfMat {
     Arr<double, MSA> savedJ, M;
 };
 template <bool REF, class T> struct MemT { using type = T; };
+// 0: grouped lanes keep private copies of the per-instance record (the host emulation of the group
+// code, whose "lanes" are threads that do not run in lockstep between the exchange points)
+#ifndef SB_GROUP_SHARED_CTL
+#define SB_GROUP_SHARED_CTL 1
+#endif
 template <class T> struct MemT<true, T> { using type = T&; };
 
 // NM = dimension of the ODE (and of the Newton matrix), NBLK = number of NM-sized blocks that are
@@ -447,7 +452,8 @@ struct Bdf {
     // per-instance state: by value (registers) with one lane per instance, references into the
     // group's shared-memory record otherwise (see BdfCtl)
     using Ctl = BdfCtl<PS>;
-    template <class T> using Mem = typename MemT<(G > 1), T>::type;
+    template <class T> using Mem = typename MemT<(G > 1) && (SB_GROUP_SHARED_CTL != 0), T>::type;
+    template <class T> using MemM = typename MemT<(G > 1), T>::type;      // the matrix rows
     // step / order control
     Mem<Arr<double, SB_LMAX + 1>> tau;
     Mem<Arr<double, SB_LMAX>> l;
@@ -458,7 +464,7 @@ struct Bdf {
     Mem<bool> jcur;
     // linear solver
     using Mat = BdfMat<MSA>;
-    Mem<Arr<double, MSA>> savedJ, M;
+    MemM<Arr<double, MSA>> savedJ, M;
     Mem<Arr<int, PS>> piv;
     // counters
     Mem<int> nst, nstlp, nstlj;

@@ -31,7 +31,11 @@ struct LaneGroup {
     struct Ids { unsigned gm; int r; };
     __device__ __forceinline__ static Ids ids() {
         Ids v;
+#ifdef SB_HOST_EMULATION
+        v.gm = mask(); v.r = rank();
+#else
         asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(v.gm), "=r"(v.r) : "r"(mask()), "r"(rank()));
+#endif
         return v;
     }
     __device__ __forceinline__ static double sum(double x, unsigned gm) {
@@ -286,7 +290,12 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     struct Rows { typename Integrator::Mat mat; double pad; };
     static_assert(sizeof(Rows) == (2 * Sys::ROW + 1) * sizeof(double), "row stride");
     __shared__ Rows rows_all[SB_BLOCK];
+#if SB_GROUP_SHARED_CTL
     Integrator bdf(sh.ctl, rows_all[threadIdx.x].mat);
+#else
+    typename Integrator::Ctl ctl_private;
+    Integrator bdf(ctl_private, rows_all[threadIdx.x].mat);
+#endif
     bdf.gid = sys.id;
     sys.yi = sh.yi;
     sys.lamv = sh.lamv;

@@ -39,7 +39,7 @@ constexpr int NP = SB_NP;
 constexpr int ND = SB_ND;
 constexpr int NP_ = SB_NP > 0 ? SB_NP : 1;
 constexpr int ND_ = SB_ND > 0 ? SB_ND : 1;
-#if defined(SB_NO_GROUP) || defined(SB_HOST_EMULATION)
+#if defined(SB_NO_GROUP) || (defined(SB_HOST_EMULATION) && !defined(SB_HOST_EMULATION_GROUP))
 constexpr int GROUP = 1;
 #else
 constexpr int GROUP = SB_GROUP_SIZE(SB_NS);
@@ -614,6 +614,9 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
 
 }  // namespace sb
 
+#ifdef SB_HOST_EMULATION_GROUP
+#include "sb_group.cuh"
+#endif
 #ifndef SB_HOST_EMULATION   // the host emulation calls the *_instance functions directly
 #include "sb_group.cuh"
 

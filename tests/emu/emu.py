@@ -55,7 +55,12 @@ def _ip(a):
 
 
 class Emulator:
-    def __init__(self, problem, workdir, defines=()):
+    def __init__(self, problem, workdir, defines=(), group=False):
+        """``group=True`` additionally builds the grouped-lane backward driver (csrc/sb_group.cuh,
+        its lanes emulated by host threads, see cuda_shim_group.h); ``adjoint(..., group=True)``
+        then runs the backward pass through it."""
+        if group:
+            defines = tuple(defines) + ('SB_HOST_EMULATION_GROUP',)
         gen = problem.generated
         self.ns, self.np, self.nd = gen.n_states, gen.n_params, gen.n_deriv
         os.makedirs(workdir, exist_ok=True)
@@ -64,7 +69,7 @@ class Emulator:
             fh.write(gen.cuda)
         out = os.path.join(workdir, 'emu_%s%s.so' % (gen.digest, ''.join('_' + d.replace('=', '') for d in defines)))
         cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
-        cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off',
+        cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-pthread', '-ffp-contract=off',
                *['-D' + d for d in defines],
                '-I', workdir, '-I', _HERE, '-I', _CSRC, os.path.join(_HERE, 'emu_main.cpp'),
                '-o', out]
@@ -118,7 +123,8 @@ class Emulator:
         return dict(y=y_out, sens=sens_out, status=status, stats=stats)
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
-                rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000, flat=None):
+                rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000, flat=None,
+                group=False):
         B0 = max(len(np.atleast_2d(y0)), len(np.atleast_2d(params)))
         tab_fused = np.zeros((B0, hist_cap, 10 + 6 * self.ns))
         fwd = self.forward(t0, tvals, y0, params, rtol, atol, hist_cap=hist_cap,
@@ -145,6 +151,10 @@ class Emulator:
                           _ip(fwd['hist_n']), _ip(fwd['status']), gptr, _dp(lam_out),
                           _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared, None, None,
                           None, None, None, None, 1, n_t + 1, 0, 32, -1 if flat is None else flat, 0, None, 0)
-        (self.lib.emu_backward if flat is None else self.lib.emu_backward_flat)(ctypes.byref(ba))
+        if group:
+            assert self.lib.emu_group_size() > 1, 'this problem does not run in lane groups'
+            self.lib.emu_backward_group(ctypes.byref(ba))
+        else:
+            (self.lib.emu_backward if flat is None else self.lib.emu_backward_flat)(ctypes.byref(ba))
         return dict(y=fwd['y'], grad=grad_out, lamda=lam_out, status=status, stats=stats,
                     fwd=fwd, tab=tab)

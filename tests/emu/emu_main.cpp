@@ -1,6 +1,15 @@
 // Entry points of the host emulation build: loop over instances instead of launching a grid.
 #define SB_HOST_EMULATION 1
 #include "cuda_shim.h"
+#ifdef SB_HOST_EMULATION_GROUP
+#include <thread>
+#include <vector>
+#include "cuda_shim_group.h"
+#define SB_GROUP_SHARED_CTL 0
+#ifndef SB_BLOCK
+#define SB_BLOCK 32
+#endif
+#endif
 #include "generated_problem.inc"     // generated __device__ functions + SB_NS/SB_NP/SB_ND
 #include "sb_kernels.cuh"
 
@@ -32,5 +41,25 @@ void emu_backward_unit(const SbBackwardArgs* a, int k0, int k1) {
     #pragma omp parallel for schedule(dynamic, 16)
     for (long long i = 0; i < a->B; ++i) sb::backward_unit<false>(*a, i, true, k0, k1);
 }
+#ifdef SB_HOST_EMULATION_GROUP
+// The grouped-lane backward driver: one group (= one instance) at a time, its lanes as threads.
+int emu_group_size() { return sb::GROUP; }
+void emu_backward_group(const SbBackwardArgs* a) {
+    constexpr int G = sb::GROUP > 1 ? sb::GROUP : 2;
+    if (sb::GROUP <= 1) return;
+    emu_group.size = G;
+    pthread_barrier_init(&emu_group.bar, nullptr, G);
+    for (long long i = 0; i < a->B; ++i) {
+        std::vector<std::thread> lanes;
+        for (int r = 0; r < G; ++r)
+            lanes.emplace_back([a, i, r]() {
+                threadIdx.x = (unsigned)r; blockDim.x = 32; blockIdx.x = 0;
+                sb::backward_unit_group<G>(*a, i, true, 0, a->n_t + 1);
+            });
+        for (auto& t : lanes) t.join();
+    }
+    pthread_barrier_destroy(&emu_group.bar);
+}
+#endif
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
 }
