@@ -299,13 +299,13 @@ class Engine:
 
 def lanes_per_instance(n_states: int) -> int:
     """Lanes of a warp that integrate one instance in the backward kernels: ``SB_GROUP_SIZE`` of
-    ``csrc/sb_args.h`` (one lane up to 4 states, then a power-of-two group with one state
-    component per lane, see ``csrc/sb_group.cuh``)."""
+    ``csrc/sb_args.h`` (one lane up to 4 states, then a power-of-two group with two state
+    components per lane, see ``csrc/sb_group.cuh``)."""
     if 'SB_NO_GROUP' in os.environ.get('SUNODE_B200_DEFINES', ''):
         return 1
-    if n_states < 5 or n_states > 32:
+    if n_states < 5 or n_states > 64:
         return 1
-    return 8 if n_states <= 8 else 16 if n_states <= 16 else 32
+    return 4 if n_states <= 8 else 8 if n_states <= 16 else 16 if n_states <= 32 else 32
 
 
 FLAT_FWD_STEPS_PER_TVAL = 8     # SB_FLAT_FWD_STEPS_PER_TVAL of csrc/sb_api.cpp

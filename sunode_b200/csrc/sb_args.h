@@ -9,13 +9,19 @@
 /* history point: (t, order, y[NS])                         -> NS + 2 doubles
  * interpolation table entry for the interval (t_lo, t_hi):
  *   [0] t_lo [1] t_hi [2] order [3] 1/delt [4..9] T[0..5] [10 + NS*j + k] Y[j][k]  -> 10 + 6*NS */
-/* Lanes of a warp that integrate one instance together (sb_group.cuh): one for small systems, a
- * power-of-two group with one state component per lane from SB_GROUP_MIN_NS states on; beyond 32
- * states one lane per instance again (loop-based LU in local memory). */
+/* Lanes of a warp that integrate one instance together (sb_group.cuh): one for small systems, from
+ * SB_GROUP_MIN_NS states on a power-of-two group whose lanes own ceil(ns / lanes) state components
+ * (and matrix rows) each -- two per lane by default (measured on the 8-state SEIR adjoint, 32 768
+ * draws: 8 lanes x 1 component 145 ms, 4 x 2 139 ms, 2 x 4 151 ms); beyond 64 states one lane per
+ * instance again (loop-based LU in local memory). */
 #ifndef SB_GROUP_MIN_NS
 #define SB_GROUP_MIN_NS 5
 #endif
-#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 2 ? 2 : (ns) <= 4 ? 4 : (ns) <= 8 ? 8 : (ns) <= 16 ? 16 : (ns) <= 32 ? 32 : 1)
+#ifdef SB_GROUP_LANES   /* experiment: a fixed group size, ceil(ns / lanes) components per lane */
+#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : SB_GROUP_LANES)
+#else
+#define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 4 ? 2 : (ns) <= 8 ? 4 : (ns) <= 16 ? 8 : (ns) <= 32 ? 16 : (ns) <= 64 ? 32 : 1)
+#endif
 
 #define SB_HIST_STRIDE(ns) ((ns) + 2)
 #define SB_TAB_STRIDE(ns) (10 + 6 * (ns))

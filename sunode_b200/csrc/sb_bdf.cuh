@@ -409,17 +409,21 @@ struct Bdf {
     // group take every branch together.  What differs from the one-lane-per-instance build is
     // confined to the hooks below: sums / maxima / votes over the group, and the linear algebra.
     static constexpr int G = Sys::GROUP;
-    static constexpr int MS = (G > 1) ? Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
-    static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;        // pivot record
-    static constexpr int MSA = (G > 1) ? (MS | 1) : MS;           // allocated (padded) row length
+    static constexpr int MS = (G > 1) ? NM * Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
+    static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;             // pivot record
+    static constexpr int MSA = (G > 1) ? ((MS + NM) | 1) : MS;         // allocated (padded) length
     typename Sys::GroupIds gid;                  // grouped lanes: lane mask + rank (empty otherwise)
     __device__ __forceinline__ double gsum(double x) const { if constexpr (G > 1) return Sys::gsum(x, gid); else return x; }
     __device__ __forceinline__ double gmax(double x) const { if constexpr (G > 1) return Sys::gmax(x, gid); else return x; }
     __device__ __forceinline__ bool gall(bool b) const { if constexpr (G > 1) return Sys::gall(b, gid); else return b; }
     // mean of the squared weighted components of a state-sized block / of a quadrature vector
     __device__ __forceinline__ double ms_y(const double* v, const double* w) const {
-        if constexpr (G > 1) { const double x = v[0] * w[0]; return gsum(x * x) * (1.0 / Sys::NS_FULL); }
-        else return wms<NM>(v, w);
+        if constexpr (G > 1) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NM; ++i) { const double x = v[i] * w[i]; s = fma(x, x, s); }
+            return gsum(s) * (1.0 / Sys::NS_FULL);
+        } else return wms<NM>(v, w);
     }
     __device__ __forceinline__ double ms_q(const double* v) const {
         if constexpr (G > 1) {

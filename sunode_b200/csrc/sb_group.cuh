@@ -83,24 +83,36 @@ struct LaneGroup {
     }
 
     // ---- dense LU across the lanes ------------------------------------------------------------
-    // Lane r < N_ holds row r of the matrix in SHARED memory, m[0..N_-1]; the rows of the lanes of a
-    // warp follow each other with a stride of STRIDE doubles (odd: conflict-free), so the row of
-    // lane w is at m + (w - r) * STRIDE and every loop below runs over run-time indices (compact
-    // code: this kernel is instruction-fetch bound).  Partial pivoting without moving rows: piv[k]
-    // is the lane whose row is the k-th pivot row.  After the factorisation a lane pivoted at step s
-    // holds the multipliers of steps < s in m[0..s-1], the RECIPROCAL pivot in m[s] and its U
-    // entries in m[s+1..].
-    template <int N_, int STRIDE>
+    // Lane r holds the C rows r*C .. r*C + C - 1 of the N_ x N_ matrix in SHARED memory: local row
+    // c at m[c * N_ .. c * N_ + N_ - 1], and in m[C * N_ + c] the elimination step at which that
+    // row was the pivot row (-1: never -- rows past N_).  The blocks of the lanes of a warp follow
+    // each other with a stride of STRIDE doubles (odd: conflict-free), so the block of lane w is at
+    // m + (w - r) * STRIDE and every loop below may use run-time indices (compact code: this
+    // kernel is instruction-fetch bound).  Partial pivoting without moving rows: piv[k] is the
+    // (global) row that is the k-th pivot row.  After the factorisation a row pivoted at step s
+    // holds the multipliers of steps < s in columns 0..s-1, the RECIPROCAL pivot in column s and
+    // its U entries in columns s+1.. .
+    template <int N_, int C, int STRIDE>
     __device__ __forceinline__ static bool lu_factor(double* m, int* piv, Ids id) {
         const int r = id.r;
         const unsigned gm = id.gm;
         bool ok = true;
-        bool used = r >= N_;                       // padding lanes hold no row
+        bool used[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            used[c] = r * C + c >= N_;             // padding rows are never pivots
+            m[C * N_ + c] = -1.0;
+        }
 #pragma unroll 1
         for (int k = 0; k < N_; ++k) {
             __syncwarp(gm);                        // the updates of step k - 1 are visible
-            double cand = used ? -1.0 : fabs(m[k]);
-            int who = r;
+            double cand = -1.0;
+            int who = r * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double v = used[c] ? -1.0 : fabs(m[c * N_ + k]);
+                if (v > cand) { cand = v; who = r * C + c; }
+            }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
                 const double oc = __shfl_xor_sync(gm, cand, o, G);
@@ -111,48 +123,65 @@ struct LaneGroup {
             }
             piv[k] = who;
             if (!(cand > 0.0)) ok = false;
-            const double* prow = m + (who - r) * STRIDE;
+            const int wlane = who / C, wrow = who - wlane * C;
+            const double* prow = m + (wlane - r) * STRIDE + wrow * N_;
             const double rp = sb_div(1.0, prow[k]);
-            const bool me = (r == who);
-            const bool elim = !used && !me;
-            const double mult = m[k] * rp;
-            if (elim) {
-                // fixed trip count with literal offsets (the row is in shared memory; the
-                // predicate replaces a loop over j = k + 1 .. N_ - 1)
 #pragma unroll
-                for (int j = 1; j < N_; ++j)
-                    if (j > k) m[j] = fma(-mult, prow[j], m[j]);
+            for (int c = 0; c < C; ++c) {
+                const bool me = (r * C + c == who);
+                if (!used[c] && !me) {
+                    // fixed trip count with literal offsets (the predicate replaces a loop over
+                    // j = k + 1 .. N_ - 1)
+                    const double mult = m[c * N_ + k] * rp;
+#pragma unroll
+                    for (int j = 1; j < N_; ++j)
+                        if (j > k) m[c * N_ + j] = fma(-mult, prow[j], m[c * N_ + j]);
+                }
             }
-            __syncwarp(gm);                        // everybody has read the pivot entry
-            if (elim) m[k] = mult;
-            if (me) { m[k] = rp; m[N_] = (double)k; }     // m[N_] (row padding): my pivot step
-            used = used || me;
+            __syncwarp(gm);                        // everybody has read the pivot row
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const bool me = (r * C + c == who);
+                if (!used[c] && !me) m[c * N_ + k] *= rp;
+                if (me) { m[c * N_ + k] = rp; m[C * N_ + c] = (double)k; }
+                used[c] = used[c] || me;
+            }
         }
-        if (r >= N_) m[N_] = -1.0;
         __syncwarp(gm);
         return ok;
     }
 
-    // b[0]: entry `rank` of the right-hand side on entry, of the solution on return
-    template <int N_>
+    // b[c]: entry r*C + c of the right-hand side on entry, of the solution on return
+    template <int N_, int C>
     __device__ __forceinline__ static void lu_solve(const double* m, const int* piv, double* b, Ids id) {
         const int r = id.r;
         const unsigned gm = id.gm;
-        const int mystep = (int)m[N_];             // the step this lane's row was the pivot row (-1: none)
-        double v = b[0];
+        int mystep[C];
+        double v[C], x[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { mystep[c] = (int)m[C * N_ + c]; v[c] = b[c]; x[c] = 0.0; }
 #pragma unroll
         for (int k = 0; k < N_; ++k) {             // L y = P b
-            const double vk = __shfl_sync(gm, v, piv[k], G);
-            v = (mystep > k) ? fma(-m[k], vk, v) : v;
+            const int p = piv[k], pl = p / C, pc = p - pl * C;
+            const double vk = __shfl_sync(gm, pick<C>(v, pc), pl, G);
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = (mystep[c] > k) ? fma(-m[c * N_ + k], vk, v[c]) : v[c];
         }
-        double x = 0.0;
 #pragma unroll
         for (int k = N_ - 1; k >= 0; --k) {        // U x = y
-            const double xk = __shfl_sync(gm, v * m[k], piv[k], G);
-            v = (mystep >= 0 && mystep < k) ? fma(-m[k], xk, v) : v;
-            x = (r == k) ? xk : x;
+            const int p = piv[k], pl = p / C, pc = p - pl * C;
+            double mine = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mine = (pc == c) ? v[c] * m[c * N_ + k] : mine;
+            const double xk = __shfl_sync(gm, mine, pl, G);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                v[c] = (mystep[c] >= 0 && mystep[c] < k) ? fma(-m[c * N_ + k], xk, v[c]) : v[c];
+                x[c] = (r * C + c == k) ? xk : x[c];
+            }
         }
-        b[0] = x;
+#pragma unroll
+        for (int c = 0; c < C; ++c) b[c] = x[c];
     }
 };
 
@@ -163,7 +192,8 @@ struct BwdSysG {
     static constexpr bool TSTOP = true;
     static constexpr int GROUP = G, NS_FULL = NS, NQ_FULL = ND_;
     static constexpr int NQL = (ND + G - 1) / G > 0 ? (ND + G - 1) / G : 1;   // quadrature components per lane
-    static_assert(NS <= G, "one state component per lane");
+    static constexpr int C = (NS + G - 1) / G;     // state components (and matrix rows) per lane:
+                                                   // lane r owns r*C .. r*C + C - 1
     const SbBackwardArgs& a;
     using GroupIds = typename LG::Ids;
     GroupIds id;           // group mask and rank of this lane
@@ -176,15 +206,17 @@ struct BwdSysG {
     __device__ __forceinline__ static double gsum(double x, GroupIds g) { return LG::sum(x, g.gm); }
     __device__ __forceinline__ static double gmax(double x, GroupIds g) { return LG::max(x, g.gm); }
     __device__ __forceinline__ static bool gall(bool b, GroupIds g) { return LG::all(b, g.gm); }
-    static constexpr int ROW = NS | 1;             // allocated row length (Bdf::MSA)
+    static constexpr int ROW = (C * NS + C) | 1;   // allocated doubles per lane and matrix (Bdf::MSA)
     __device__ __forceinline__ void add_identity(double* m) const {
-        if (id.r < NS) m[id.r] += 1.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (id.r * C + c < NS) m[c * NS + id.r * C + c] += 1.0;
     }
     __device__ __forceinline__ bool lu_factor(double* m, int* piv) const {
-        return LG::template lu_factor<NS, 2 * ROW + 1>(m, piv, id);
+        return LG::template lu_factor<NS, C, 2 * ROW + 1>(m, piv, id);
     }
     __device__ __forceinline__ void lu_solve(const double* m, const int* piv, double* b) const {
-        LG::template lu_solve<NS>(m, piv, b, id);
+        LG::template lu_solve<NS, C>(m, piv, b, id);
     }
 
     const double* p;       // this instance's parameters (global memory, read where needed)
@@ -201,9 +233,11 @@ struct BwdSysG {
     __device__ __forceinline__ void set_time(double t_) {
         t = t_;
         const int r = id.r;
-        const int col = r < NS ? r : 0;
+        int col[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) col[c] = r * C + c < NS ? r * C + c : 0;
         const double* e = tab + (size_t)idx * TAB_STRIDE;
-        double lo, hi, inv_delt, T[SB_QMAX], Y[SB_LMAX];
+        double lo, hi, inv_delt, T[SB_QMAX], Y[SB_LMAX][C];
         int order;
         bool went_left = false;
 #pragma unroll 1
@@ -214,27 +248,36 @@ struct BwdSysG {
 #pragma unroll
             for (int i = 0; i < SB_QMAX; ++i) T[i] = __ldg(e + 4 + i);
 #pragma unroll
-            for (int j = 0; j < SB_LMAX; ++j) Y[j] = __ldg(e + 10 + NS * j + col);
+            for (int j = 0; j < SB_LMAX; ++j)
+#pragma unroll
+                for (int c = 0; c < C; ++c) Y[j][c] = __ldg(e + 10 + NS * j + col[c]);
             // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
             if ((t < lo || (went_left && t <= lo)) && idx > 1) { --idx; e -= TAB_STRIDE; went_left = true; }
             else if (t > hi && idx < np - 1 && !went_left) { ++idx; e += TAB_STRIDE; }
             else break;
         }
-        double mine = Y[0];
-        double c = 1.0;
+        double mine[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) mine[c] = Y[0][c];
+        double w = 1.0;
 #pragma unroll
         for (int i = 0; i < SB_QMAX; ++i) {
-            c = (i < order) ? c * ((t - T[i]) * inv_delt) : 0.0;
-            mine = fma(c, Y[i + 1], mine);
+            w = (i < order) ? w * ((t - T[i]) * inv_delt) : 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) mine[c] = fma(w, Y[i + 1][c], mine[c]);
         }
         __syncwarp(id.gm);                        // the previous values have been consumed
-        if (r < NS) yi[r] = mine;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (r * C + c < NS) yi[r * C + c] = mine[c];
         __syncwarp(id.gm);
     }
     // every lane contributes its component; the generated functions then read what they need
     __device__ __forceinline__ void gather(const double* mine) const {
         __syncwarp(id.gm);                        // the previous contents have been consumed
-        if (id.r < NS) lamv[id.r] = mine[0];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (id.r * C + c < NS) lamv[id.r * C + c] = mine[c];
         __syncwarp(id.gm);
     }
     // every lane evaluates the whole (cheap) function and keeps its own component
@@ -242,16 +285,19 @@ struct BwdSysG {
         double out[NS];
         gather(lam_mine);
         sb_adj_rhs(t, yi, lamv, p, out);
-        out_mine[0] = LG::template pick<NS>(out, id.r);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out_mine[c] = LG::template pick<NS>(out, id.r * C + c);
     }
     __device__ __forceinline__ void jac(const double*, double* Jrow) const {
         double J[NS * NS];
         sb_adj_jac(t, yi, p, J);
         const int r = id.r;
-        static_for<0, NS>([&](auto J_) {
-            constexpr int j = SB_IDX(J_);
-            Jrow[j] = LG::template pick<NS>(J + NS * j, r);     // column-major: J[r + NS*j]
-        });
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            static_for<0, NS>([&](auto J_) {
+                constexpr int j = SB_IDX(J_);
+                Jrow[c * NS + j] = LG::template pick<NS>(J + NS * j, r * C + c);     // column-major: J[row + NS*j]
+            });
     }
     __device__ __forceinline__ void quad(const double* lam_mine, double* out_mine) const {
         double out[ND_];
@@ -273,12 +319,15 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     using Sys = BwdSysG<G>;
     using LG = LaneGroup<G>;
     constexpr int NQL = Sys::NQL;
-    using Integrator = Bdf<1, (ND > 0 ? NQL : 0), Sys>;
+    constexpr int C = Sys::C;
+    using Integrator = Bdf<C, (ND > 0 ? NQL : 0), Sys>;
     if (!valid) inst = 0;
     Sys sys(a);
     const int r = sys.id.r;
     const unsigned gm = sys.id.gm;
-    const bool has_y = r < NS;
+    bool has_y[C];                              // the state components this lane owns
+#pragma unroll
+    for (int c = 0; c < C; ++c) has_y[c] = r * C + c < NS;
     const bool first = k_begin == 0, last = k_end == a.n_t + 1;
     const int np = a.hist_n[inst];
 
@@ -299,19 +348,21 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     bdf.gid = sys.id;
     sys.yi = sh.yi;
     sys.lamv = sh.lamv;
-    double lam[1], quad[NQL];
+    double lam[C], quad[NQL];
     int status;
     bdf.clear_stats();
     sys.idx = np > 1 ? np - 1 : 1;
     if (first) {
         status = a.fwd_status ? a.fwd_status[inst] : SB_SUCCESS;
-        lam[0] = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) lam[c] = 0.0;
 #pragma unroll
         for (int c = 0; c < NQL; ++c) quad[c] = 0.0;
     } else {
         const double* cd = a.carry_d + (size_t)inst * (NS + ND_);
         const int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
-        lam[0] = has_y ? cd[r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) lam[c] = has_y[c] ? cd[r * C + c] : 0.0;
 #pragma unroll
         for (int c = 0; c < NQL; ++c) quad[c] = (r + G * c < ND) ? cd[NS + r + G * c] : 0.0;
         status = ci[0]; sys.idx = ci[1];
@@ -372,11 +423,16 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
         }
         if (valid && k < a.n_t) {
             const double* g = g_base + (size_t)(a.n_t - 1 - k) * NS;
-            if (has_y) lam[0] -= g[r];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (has_y[c]) lam[c] -= g[r * C + c];
             if (a.lamda_all || a.quad_all) {
                 const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
                 const bool ok = status == SB_SUCCESS;
-                if (a.lamda_all && has_y) a.lamda_all[row * NS + r] = ok ? lam[0] : qnan();
+                if (a.lamda_all)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (has_y[c]) a.lamda_all[row * NS + r * C + c] = ok ? lam[c] : qnan();
                 if (a.quad_all)
 #pragma unroll
                     for (int c = 0; c < NQL; ++c)
@@ -390,7 +446,9 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     if (!last) {
         double* cd = a.carry_d + (size_t)inst * (NS + ND_);
         int* ci = a.carry_i + (size_t)inst * SB_CARRY_INTS;
-        if (has_y) cd[r] = lam[0];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (has_y[c]) cd[r * C + c] = lam[c];
 #pragma unroll
         for (int c = 0; c < NQL; ++c)
             if (r + G * c < ND) cd[NS + r + G * c] = quad[c];
@@ -402,7 +460,9 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
         return;
     }
     const bool bad = status != SB_SUCCESS;
-    if (has_y) a.lamda_out[inst * NS + r] = bad ? qnan() : lam[0];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if (has_y[c]) a.lamda_out[inst * NS + r * C + c] = bad ? qnan() : lam[c];
 #pragma unroll
     for (int c = 0; c < NQL; ++c)
         if (r + G * c < ND) a.grad_out[inst * ND + r + G * c] = bad ? qnan() : quad[c];

@@ -26,7 +26,7 @@
 #define SB_TAB_PREFETCH_MAX_NS 4
 #endif
 #ifndef SB_GROUP_MIN_BLOCKS
-#define SB_GROUP_MIN_BLOCKS (512 / SB_BLOCK)   /* grouped lanes: 16 warps per SM, <= 128 registers */
+#define SB_GROUP_MIN_BLOCKS (384 / SB_BLOCK)   /* grouped lanes: 12 warps per SM, <= 168 registers */
 #endif
 #ifndef SB_FLAT_IDLE
 #define SB_FLAT_IDLE 16     /* mean passes a lane may wait per interval before the warp goes flat */

@@ -142,8 +142,9 @@ def test_flat_interval_schedule_is_the_same_computation(name, tmp_path):
 
 
 def test_lane_group_code_matches_one_lane_per_instance(tmp_path):
-    """csrc/sb_group.cuh on the host: the 8 lanes of a SEIR instance are 8 threads, shuffles and
-    __syncwarp are barrier rendezvous (tests/emu/cuda_shim_group.h).  The cross-lane LU, the
+    """csrc/sb_group.cuh on the host: the lanes of a SEIR instance are threads, shuffles and
+    __syncwarp are barrier rendezvous (tests/emu/cuda_shim_group.h); checked for 4 lanes x 2 state
+    components (the default), 8 x 1 and 2 x 4.  The cross-lane LU, the
     butterfly norms and the shared-memory exchange must reproduce the one-lane-per-instance
     integrator: same step sequence but for rounding-level flips, gradients to 1e-9."""
     w = examples.workloads()['seir_adj']
@@ -151,12 +152,17 @@ def test_lane_group_code_matches_one_lane_per_instance(tmp_path):
     B = 6
     y0, theta = w.draws(B)
     grads = np.random.default_rng(12).standard_normal((B, len(w.tvals), prob.n_states))
-    emu = Emulator(prob, str(tmp_path), group=True)
-    one = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512)
-    grp = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512, group=True)
-    assert (one['status'] == 0).all() and (grp['status'] == 0).all()
-    assert np.max(np.abs(grp['grad'] - one['grad']) / np.abs(one['grad']).max(axis=0)) <= 1e-9
-    assert np.max(np.abs(grp['lamda'] - one['lamda']) / np.abs(one['lamda']).max(axis=0)) <= 1e-9
-    steps_one, steps_grp = one['stats'][:, 0], grp['stats'][:, 0]
-    assert np.max(np.abs(steps_one - steps_grp) / steps_one) <= 0.01
-    np.testing.assert_array_equal(one['stats'][:, 7], grp['stats'][:, 7])      # stored points
+    one = None
+    for lanes in (None, 8, 2):
+        defines = () if lanes is None else ('SB_GROUP_LANES=%d' % lanes,)
+        emu = Emulator(prob, str(tmp_path), defines=defines, group=True)
+        assert emu.lib.emu_group_size() == (lanes or 4)
+        if one is None:
+            one = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512)
+        grp = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512, group=True)
+        assert (one['status'] == 0).all() and (grp['status'] == 0).all()
+        assert np.max(np.abs(grp['grad'] - one['grad']) / np.abs(one['grad']).max(axis=0)) <= 1e-9
+        assert np.max(np.abs(grp['lamda'] - one['lamda']) / np.abs(one['lamda']).max(axis=0)) <= 1e-9
+        steps_one, steps_grp = one['stats'][:, 0], grp['stats'][:, 0]
+        assert np.max(np.abs(steps_one - steps_grp) / steps_one) <= 0.01
+        np.testing.assert_array_equal(one['stats'][:, 7], grp['stats'][:, 7])      # stored points

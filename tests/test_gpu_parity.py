@@ -288,8 +288,8 @@ def test_interval_schedule_is_transparent(monkeypatch):
 
 
 def test_lane_groups_match_one_lane_per_instance(monkeypatch):
-    """SEIR (8 states) runs with 8 lanes per instance (sb_group.cuh: one state component per lane,
-    LU across the lanes with shuffles, norms as butterfly sums).  Same algorithm as the
+    """SEIR (8 states) runs with 4 lanes per instance (sb_group.cuh: two state components and
+    matrix rows per lane, LU across the lanes with shuffles, norms as butterfly sums).  Same algorithm as the
     one-lane-per-instance build (-DSB_NO_GROUP), different summation order in the norms: the step
     sequences agree but for rounding-level decision flips and the results to 1e-9; segmentation
     is bit-transparent in group mode too; batch sizes that leave groups / warps partly empty."""
