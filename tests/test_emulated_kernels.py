@@ -98,8 +98,10 @@ def test_edge_cases_match_oracle(tmp_path):
 
 
 def test_ten_state_chain_uses_loop_lu(tmp_path):
-    """A 10-state linear reaction chain: exercises the loop-based (run-time indexed) LU that
-    takes over beyond 8 states, against the oracle."""
+    """A 10-state linear reaction chain: exercises the loop-based (run-time indexed) LU that the
+    one-lane-per-instance build uses beyond 8 states (forward kernel, SB_NO_GROUP backward), and the
+    grouped backward kernel with 8 lanes x 2 components of which 6 are padding (one state and one
+    parameter: a single quadrature component for 8 lanes); both against the oracle."""
     from sunode_b200 import SympyProblem
 
     def rhs(t, y, p):
@@ -115,12 +117,15 @@ def test_ten_state_chain_uses_loop_lu(tmp_path):
     y0 = np.zeros((4, 10)); y0[:, 0] = 1.0
     k = np.array([[0.5], [1.0], [2.0], [4.0]])
     g = np.random.default_rng(0).standard_normal((8, 10))
-    r = Emulator(prob, str(tmp_path)).adjoint(0.0, tv, y0, k, g, 1e-8, 1e-8, hist_cap=512)
+    emu = Emulator(prob, str(tmp_path), group=True)
+    assert emu.lib.emu_group_size() == 8
     yo, go, lo, so, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(0.0, tv, y0, k, g)
-    assert (r['status'] == 0).all() and (so == 0).all()
-    assert np.max(np.abs(r['y'] - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
-    np.testing.assert_allclose(r['grad'], go, rtol=1e-7)
-    np.testing.assert_allclose(r['lamda'], lo, rtol=1e-7, atol=1e-12)
+    for group in (False, True):
+        r = emu.adjoint(0.0, tv, y0, k, g, 1e-8, 1e-8, hist_cap=512, group=group)
+        assert (r['status'] == 0).all() and (so == 0).all()
+        assert np.max(np.abs(r['y'] - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
+        np.testing.assert_allclose(r['grad'], go, rtol=1e-7)
+        np.testing.assert_allclose(r['lamda'], lo, rtol=1e-7, atol=1e-12)
 
 
 @pytest.mark.parametrize('name', ['lv_adj', 'robertson_adj'])

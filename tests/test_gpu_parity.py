@@ -326,3 +326,32 @@ def test_lane_groups_match_one_lane_per_instance(monkeypatch):
         assert np.max(np.abs(g[2] - t[2]) / np.abs(t[2]).max(axis=0)) <= 1e-9
         if B > 100:
             assert (g[4][:, 0] == t[4][:, 0]).mean() >= 0.9           # backward step counts
+
+
+def test_ten_state_chain_grouped_lanes_with_padding():
+    """10 states, 1 parameter: the grouped backward kernel with 8 lanes x 2 components (6 padding
+    rows, one quadrature component for 8 lanes) and the one-lane forward kernel with the loop-based
+    LU, against the oracle; a batch that leaves groups and warps partly empty."""
+    from sunode_b200 import SympyProblem
+
+    def rhs(t, y, p):
+        x = y.x
+        out = []
+        for i in range(10):
+            inflow = p.k * x[i - 1] if i > 0 else 0
+            out.append(inflow - p.k * (1 + 0.1 * i) * x[i])
+        return {'x': out}
+
+    prob = SympyProblem({'k': ()}, {'x': 10}, rhs, [('k',)])
+    tv = np.linspace(0.2, 3.0, 8)
+    B = 11
+    y0 = np.zeros((B, 10)); y0[:, 0] = 1.0
+    k = np.linspace(0.4, 4.0, B)[:, None]
+    g = np.random.default_rng(0).standard_normal((8, 10))
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    y, grad, lam, st = solver.solve_adjoint_batch(0.0, tv, y0, k, g)
+    yo, go, lo, so, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(0.0, tv, y0, k, g)
+    assert (st == 0).all() and (so == 0).all()
+    assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
+    np.testing.assert_allclose(grad, go, rtol=1e-7)
+    np.testing.assert_allclose(lam, lo, rtol=1e-7, atol=1e-12)
