@@ -350,7 +350,7 @@ def test_ten_state_chain_grouped_lanes_with_padding():
     g = np.random.default_rng(0).standard_normal((8, 10))
     solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
     y, grad, lam, st = solver.solve_adjoint_batch(0.0, tv, y0, k, g)
-    yo, go, lo, so, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(0.0, tv, y0, k, g)
+    yo, go, lo, so, _ = _oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(0.0, tv, y0, k, g)
     assert (st == 0).all() and (so == 0).all()
     assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
     np.testing.assert_allclose(grad, go, rtol=1e-7)
