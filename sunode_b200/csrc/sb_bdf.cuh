@@ -411,7 +411,10 @@ struct Bdf {
     static constexpr int G = Sys::GROUP;
     static constexpr int MS = (G > 1) ? NM * Sys::NS_FULL : NM * NM;   // matrix entries a lane holds
     static constexpr int PS = (G > 1) ? Sys::NS_FULL : NM;             // pivot record
-    static constexpr int MSA = (G > 1) ? ((MS + NM) | 1) : MS;         // allocated (padded) length
+    // one-lane build: the two matrices may live in shared memory as well (Sys::MAT_SHARED), which
+    // frees 4 NM^2 registers where the integrator state no longer fits (3-4 states)
+    static constexpr bool MAT_REF = (G > 1) || Sys::MAT_SHARED;
+    static constexpr int MSA = (G > 1) ? ((MS + NM) | 1) : (Sys::MAT_SHARED ? (MS | 1) : MS);   // allocated length
     typename Sys::GroupIds gid;                  // grouped lanes: lane mask + rank (empty otherwise)
     __device__ __forceinline__ double gsum(double x) const { if constexpr (G > 1) return Sys::gsum(x, gid); else return x; }
     __device__ __forceinline__ double gmax(double x) const { if constexpr (G > 1) return Sys::gmax(x, gid); else return x; }
@@ -457,7 +460,7 @@ struct Bdf {
     // group's shared-memory record otherwise (see BdfCtl)
     using Ctl = BdfCtl<PS>;
     template <class T> using Mem = typename MemT<(G > 1) && (SB_GROUP_SHARED_CTL != 0), T>::type;
-    template <class T> using MemM = typename MemT<(G > 1), T>::type;      // the matrix rows
+    template <class T> using MemM = typename MemT<MAT_REF, T>::type;      // the matrix rows
     // step / order control
     Mem<Arr<double, SB_LMAX + 1>> tau;
     Mem<Arr<double, SB_LMAX>> l;

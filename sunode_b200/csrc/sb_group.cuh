@@ -191,6 +191,7 @@ struct BwdSysG {
     using LG = LaneGroup<G>;
     static constexpr bool TSTOP = true;
     static constexpr int GROUP = G, NS_FULL = NS, NQ_FULL = ND_;
+    static constexpr bool MAT_SHARED = true;
     static constexpr int NQL = (ND + G - 1) / G > 0 ? (ND + G - 1) / G : 1;   // quadrature components per lane
     static constexpr int C = (NS + G - 1) / G;     // state components (and matrix rows) per lane:
                                                    // lane r owns r*C .. r*C + C - 1

@@ -57,6 +57,7 @@ template <int NBLK>
 struct FwdSysT {
     static constexpr bool TSTOP = false;
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = 1;
+    static constexpr bool MAT_SHARED = false;
     struct GroupIds {};
     const SbForwardArgs& a;
     double p[NP_];
@@ -280,6 +281,15 @@ __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long lo
 struct BwdSys {
     static constexpr bool TSTOP = true;
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = ND_;
+    // saved Jacobian + Newton matrix in shared memory (2..4 states; measured: LV backward 17.76 ->
+    // 16.78 ms, the 16 registers end the spilling; Robertson 208 -> 193 ms).  From 5 states on the
+    // grouped build takes over; the one-lane build of such systems (SB_NO_GROUP, > 64 states)
+    // keeps them in registers / local memory, a row per lane would not fit in shared memory.
+#if defined(SB_HOST_EMULATION) || defined(SB_MAT_IN_REGISTERS)
+    static constexpr bool MAT_SHARED = false;
+#else
+    static constexpr bool MAT_SHARED = NS >= 2 && NS <= 4;
+#endif
     struct GroupIds {};
     const SbBackwardArgs& a;
     __device__ __forceinline__ explicit BwdSys(const SbBackwardArgs& a_) : a(a_) {}
@@ -367,6 +377,21 @@ struct BwdSys {
     __device__ __forceinline__ void quad(const double* lam, double* out) const { sb_quad_rhs(t, yi, lam, p, out); }
 };
 
+// Where the one-lane backward integrator keeps its two matrices: registers, or (BwdSys::MAT_SHARED)
+// a per-lane slot of shared memory, an odd number of doubles apart (conflict-free).
+template <class Mat, bool SHARED>
+__device__ __forceinline__ Mat& mat_home(Mat& in_registers) {
+#ifndef SB_HOST_EMULATION
+    if constexpr (SHARED) {
+        struct Slot { Mat mat; double pad; };
+        static_assert((sizeof(Slot) / sizeof(double)) % 2 == 1, "odd stride");
+        __shared__ Slot slots[SB_BLOCK];
+        return slots[threadIdx.x].mat;
+    } else
+#endif
+    return in_registers;
+}
+
 // Backward: the reference restarts the backward integrator at every output time
 // (CVodeReInitB + CVodeQuadReInitB, solver.py:756-757).  Because of those restarts NOTHING of the
 // integrator survives an interval: only lamda, the quadrature, the status and the table position
@@ -397,11 +422,12 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
 
 #ifdef SB_CTL_ZERO_INIT
     typename Integrator::Ctl ctl{};
-    typename Integrator::Mat mat{};
+    typename Integrator::Mat mat_regs{};
 #else
     typename Integrator::Ctl ctl;      // every field is set by reinit() / the first setup before use
-    typename Integrator::Mat mat;
+    typename Integrator::Mat mat_regs;
 #endif
+    typename Integrator::Mat& mat = mat_home<typename Integrator::Mat, BwdSys::MAT_SHARED>(mat_regs);
     Integrator bdf(ctl, mat);
     BwdSys sys(a);
     double lam[NS], quad[ND_];
