@@ -28,6 +28,23 @@ def _one_fixed(t, y, p):
     return {'x': p.r * y.x * (1 - y.x / p.K) + sym.sqrt(y.x)}
 
 
+def _seir(t, y, p):
+    # BASELINE configs[4] (sunode_b200/examples.py: two-group SEIR, nested states, all six
+    # parameters differentiated)
+    out = {}
+    betas = (p.beta1, p.beta2)
+    groups = (y.g1, y.g2)
+    for k, name in enumerate(('g1', 'g2')):
+        g, h = groups[k], groups[1 - k]
+        lam = betas[k] * g.I + p.kappa * h.I
+        out[name] = {'S': -g.S * lam + p.omega * g.R, 'E': g.S * lam - p.sigma * g.E,
+                     'I': p.sigma * g.E - p.gamma * g.I, 'R': p.gamma * g.I - p.omega * g.R}
+    return out
+
+
+_SEIR_PARAMS = ['beta1', 'beta2', 'kappa', 'sigma', 'gamma', 'omega']
+_SEIR_GROUP = {'S': (), 'E': (), 'I': (), 'R': ()}
+
 CASES = {
     'lv': ({'alpha': (), 'beta': (), 'gamma': (), 'delta': ()}, {'hares': (), 'lynx': ()}, _lv,
            [('alpha',), ('beta',)]),
@@ -35,4 +52,7 @@ CASES = {
                   [('k1',), ('k2',), ('k3',)]),
     'nested': ({'c': {'d': 3}, 'f': 4}, {'a': 3, 'b': {'c': 2}}, _nested, [('c', 'd')]),
     'one_fixed': ({'r': (), 'K': ()}, {'x': ()}, _one_fixed, [('K',)]),
+    # appended last: the generator draws its inputs sequentially, earlier cases keep their vectors
+    'seir': ({n: () for n in _SEIR_PARAMS}, {'g1': dict(_SEIR_GROUP), 'g2': dict(_SEIR_GROUP)}, _seir,
+             [(n,) for n in _SEIR_PARAMS]),
 }
