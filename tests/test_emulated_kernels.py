@@ -171,3 +171,25 @@ def test_lane_group_code_matches_one_lane_per_instance(tmp_path):
         steps_one, steps_grp = one['stats'][:, 0], grp['stats'][:, 0]
         assert np.max(np.abs(steps_one - steps_grp) / steps_one) <= 0.01
         np.testing.assert_array_equal(one['stats'][:, 7], grp['stats'][:, 7])      # stored points
+
+
+def test_double_integrator_zero_error_estimates(tmp_path):
+    """SURVEY G2 (from_sympy.ipynb cells 39-41) through the device code: the solution is a
+    quadratic, the local error estimates are exactly zero from order 2 on, so the step-size ratio
+    takes its zero / out-of-range branch (eta_root2's slow path) and the step grows by etamax."""
+    from tests.test_oracle import _double_integrator, _double_integrator_closed_form
+    prob = _double_integrator()
+    tvals = np.arange(1, 10).astype(float)
+    rng = np.random.default_rng(41)
+    B = 4
+    P, Y0 = rng.standard_normal((B, 3)), rng.standard_normal((B, 2))
+    emu = Emulator(prob, str(tmp_path))
+    fwd = emu.forward(0.0, tvals, Y0, P, 1e-10, 1e-10)
+    grads = 2 * fwd['y']
+    r = emu.adjoint(0.0, tvals, Y0, P, grads, 1e-10, 1e-10, hist_cap=512)
+    assert (r['status'] == 0).all()
+    for b in range(B):
+        sol, loss, grad_p, grad_y0 = _double_integrator_closed_form(tvals, Y0[b], P[b])
+        np.testing.assert_allclose(r['y'][b], sol, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r['grad'][b], grad_p, rtol=1e-8, atol=1e-8 * abs(grad_p[1]))
+        np.testing.assert_allclose(-r['lamda'][b], grad_y0, rtol=1e-8, atol=1e-8 * np.abs(grad_y0).max())

@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/cvodes_port.c).  The reference's tests hold no numeric assertions
 for this path and SUNDIALS is absent, so the pins are:
   G1  the one recorded CVODES run the reference ships (notebooks/from_sympy.ipynb:240-242),
+  G2  the property its notebook records for the adjoint (cells 39-41: equals the closed form),
   G3  the closed form of the reference's smoke-test problem (sunode/test_solve.py:81-154),
   G4  the README Lotka-Volterra problem against SciPy DOP853 at 1e-13,
   G5  SciPy's VODE-BDF (CVODE's ancestor) step counts, finite differences of a tight solve."""
@@ -164,3 +165,41 @@ def test_t0_in_tvals_and_structure_of_outputs():
     y, status, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_forward(
         0.0, tvals, (1.0, 0.1), (0.1, 0.2, 0.3, 0.4))
     np.testing.assert_array_equal(y[0, 0], [1.0, 0.1])
+
+
+def _double_integrator():
+    """The problem behind from_sympy.ipynb cells 39-41: x' = v, v' = p_b, three
+    parameters of which only p_b acts; solution x = p_b t^2/2 + v0 t + x0, v = p_b t + v0."""
+    return SympyProblem(params={'a': (), 'b': (), 'c': ()}, states={'x': (), 'v': ()},
+                        rhs_sympy=lambda t, y, p: {'x': y.v, 'v': p.b},
+                        derivative_params=[('a',), ('b',), ('c',)])
+
+
+def _double_integrator_closed_form(tvals, y0, p):
+    x = 0.5 * tvals ** 2 * p[1] + tvals * y0[1] + y0[0]
+    v = tvals * p[1] + y0[1]
+    loss = np.sum(x ** 2 + v ** 2)
+    grad_p = np.array([0.0, np.sum(2 * x * 0.5 * tvals ** 2 + 2 * v * tvals), 0.0])
+    grad_y0 = np.array([np.sum(2 * x), np.sum(2 * x * tvals + 2 * v)])
+    return np.stack([x, v], axis=1), loss, grad_p, grad_y0
+
+
+def test_g2_adjoint_equals_closed_form_of_double_integrator():
+    """Property recorded in the reference's notebook (from_sympy.ipynb cells 39-41: the adjoint
+    loss / gradients equal the analytic ones to ~1e-11 relative, inputs unseeded randn): the
+    oracle on seeded draws.  The solution is a polynomial of degree 2, so from order 2 on the
+    local error estimate is exactly zero -- the controller's zero-error branch is exercised too."""
+    prob = _double_integrator()
+    tvals = np.arange(1, 10).astype(float)
+    rng = np.random.default_rng(41)
+    orc = Oracle(prob, rtol=1e-10, atol=1e-10)
+    for _ in range(4):
+        p, y0 = rng.standard_normal(3), rng.standard_normal(2)
+        sol, loss, grad_p, grad_y0 = _double_integrator_closed_form(tvals, y0, p)
+        y, _, _ = orc.solve_forward(0.0, tvals, y0, p)
+        np.testing.assert_allclose(y[0], sol, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(np.sum(y[0] ** 2), loss, rtol=1e-9)
+        _, grad, lam, status, _ = orc.solve_adjoint(0.0, tvals, y0, p, 2 * y[0])
+        assert status[0] == 0
+        np.testing.assert_allclose(grad[0], grad_p, rtol=1e-8, atol=1e-8 * abs(grad_p[1]))
+        np.testing.assert_allclose(-lam[0], grad_y0, rtol=1e-8, atol=1e-8 * np.abs(grad_y0).max())
