@@ -203,3 +203,36 @@ def test_g2_adjoint_equals_closed_form_of_double_integrator():
         assert status[0] == 0
         np.testing.assert_allclose(grad[0], grad_p, rtol=1e-8, atol=1e-8 * abs(grad_p[1]))
         np.testing.assert_allclose(-lam[0], grad_y0, rtol=1e-8, atol=1e-8 * np.abs(grad_y0).max())
+
+
+@pytest.mark.parametrize('name,env', [('robertson_adj', 2000.0), ('seir_adj', 300.0)])
+def test_g5_stiff_and_larger_systems_against_independent_solvers(name, env):
+    """SURVEY G5 for the workloads without a closed form: the oracle's trajectories at
+    rtol = atol = 1e-8 against SciPy's Radau (an implicit Runge-Kutta method, no code or algorithm
+    shared with BDF) at 1e-12, median draw and two perturbed ones; envelope in tolerance units
+    (the stiff problem's global error is a few hundred local tolerances, as for VODE-BDF)."""
+    import sympy
+    w = examples.workloads()[name]
+    prob = w.make_problem()
+    y0s, thetas = w.draws(2)
+    cases = [(np.asarray(w.y0, float), np.asarray(w.theta_med, float))] + list(zip(y0s, thetas))
+    gen = prob.host_functions
+    n_s = prob.n_states
+    for y0, theta in cases:
+        def f(t, y):
+            out = np.zeros(n_s)
+            gen.rhs(t, np.ascontiguousarray(y), theta, out)
+            return out
+
+        def jac(t, y):
+            J = np.zeros(n_s * n_s)
+            gen.jac(t, np.ascontiguousarray(y), theta, J)
+            return J.reshape(n_s, n_s).T                     # ours is column-major
+        sol = solve_ivp(f, (w.t0, w.tvals[-1]), y0, method='Radau', jac=jac, t_eval=w.tvals,
+                        rtol=1e-12, atol=1e-14)
+        assert sol.success
+        truth = sol.y.T
+        y, status, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_forward(w.t0, w.tvals, y0, theta)
+        assert status[0] == 0
+        err = np.max(np.abs(y[0] - truth) / (1e-8 * np.abs(truth) + 1e-8))
+        assert err <= env, (name, err)
