@@ -62,4 +62,9 @@ void emu_backward_group(const SbBackwardArgs* a) {
 }
 #endif
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
+// sizeof the argument blocks as the C++ side sees them (checked against the ctypes mirrors)
+void emu_arg_sizes(int* fwd, int* tab, int* bwd, int* ev) {
+    *fwd = (int)sizeof(SbForwardArgs); *tab = (int)sizeof(SbTablesArgs);
+    *bwd = (int)sizeof(SbBackwardArgs); *ev = (int)sizeof(SbEvalArgs);
+}
 }

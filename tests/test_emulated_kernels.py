@@ -193,3 +193,16 @@ def test_double_integrator_zero_error_estimates(tmp_path):
         np.testing.assert_allclose(r['y'][b], sol, rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(r['grad'][b], grad_p, rtol=1e-8, atol=1e-8 * abs(grad_p[1]))
         np.testing.assert_allclose(-r['lamda'][b], grad_y0, rtol=1e-8, atol=1e-8 * np.abs(grad_y0).max())
+
+
+def test_argument_blocks_match_their_ctypes_mirrors(tmp_path):
+    """csrc/sb_args.h is shared by the launcher and the device code; the emulation reaches the
+    device code through ctypes mirrors of those structs, which must not drift."""
+    import ctypes
+    from tests.emu import emu as E
+    em = Emulator(examples.lotka_volterra(), str(tmp_path))
+    sizes = [ctypes.c_int() for _ in range(4)]
+    em.lib.emu_arg_sizes(*[ctypes.byref(s) for s in sizes])
+    assert sizes[0].value == ctypes.sizeof(E.ForwardArgs)
+    assert sizes[1].value == ctypes.sizeof(E.TablesArgs)
+    assert sizes[2].value == ctypes.sizeof(E.BackwardArgs)
