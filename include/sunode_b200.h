@@ -46,6 +46,9 @@ typedef struct sb_problem sb_problem;
 int sb_version(void);
 const char* sb_last_error(void);
 int sb_device_count(int* count);
+/* Version of the NVRTC that sb_compile uses (the toolkit's, /usr/local/cuda/lib64, unless
+ * SUNODE_B200_NVRTC names another library); part of the cubin cache key of the Python layer. */
+int sb_nvrtc_version(int* major, int* minor);
 
 /* JIT-compile the generated problem functions (CUDA flavour of SympyProblem.generated) together
  * with the integrator kernels embedded in this library into a cubin for `arch` ("sm_100a").

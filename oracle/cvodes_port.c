@@ -130,8 +130,11 @@ typedef struct {
     int cap;
     double* t;       /* [cap] */
     double* y;       /* [cap][ns] */
+    double* yd;      /* [cap][ns] y' = zn[1] / h (CV_HERMITE only, else NULL) */
     int* order;      /* [cap] */
     int ns;
+    int hermite;     /* CV_HERMITE instead of CV_POLYNOMIAL (solver.py:581-586) */
+    double Y0h[NMAX], Y1h[NMAX];   /* CVAhermiteGetY's cached Y[0], Y[1] */
     /* interpolation cache */
     int ilast, newdata;
     int ord_cached;
@@ -931,7 +934,7 @@ static int fwd_rhs(cv_mem* m, double t, const double* y, double* ydot) { return 
 static int fwd_jac(cv_mem* m, double t, const double* y, double* J) { return m->prob->jac(t, y, m->p, J); }
 
 /* ---- adjoint data store: CVApolynomialStorePnt / CVAfindIndex / CVApolynomialGetY -------------- */
-static int hist_store(hist_t* H, long idx, double t, const double* y, int order) {
+static int hist_store(hist_t* H, long idx, double t, const double* y, int order, const double* yd) {
     /* CVodeF writes the point of step nst at dt_mem[nst] (cvodea.c: "Load next point in dt_mem");
      * a CVode(CV_ONE_STEP) call that only reports an already-taken step rewrites the same slot. */
     if (idx >= H->cap) {
@@ -941,10 +944,15 @@ static int hist_store(hist_t* H, long idx, double t, const double* y, int order)
         H->y = (double*)realloc(H->y, sizeof(double) * ncap * H->ns);
         H->order = (int*)realloc(H->order, sizeof(int) * ncap);
         if (!H->t || !H->y || !H->order) return -1;
+        if (H->hermite) {
+            H->yd = (double*)realloc(H->yd, sizeof(double) * ncap * H->ns);
+            if (!H->yd) return -1;
+        }
         H->cap = ncap;
     }
     H->t[idx] = t;
     memcpy(H->y + (size_t)idx * H->ns, y, sizeof(double) * H->ns);
+    if (H->hermite) memcpy(H->yd + (size_t)idx * H->ns, yd, sizeof(double) * H->ns);
     H->order[idx] = order;
     if (idx + 1 > H->np) H->np = (int)idx + 1;
     return 0;
@@ -981,6 +989,28 @@ static int hist_get_y(hist_t* H, double t, double* y) {
     } else indx = H->ilast;
 
     if (indx == 0) { memcpy(y, H->y, sizeof(double) * ns); return 0; }
+
+    if (H->hermite) {
+        /* CVAhermiteGetY: cubic through (y, y') at the two ends of the stored step */
+        double t0 = H->t[indx - 1], t1 = H->t[indx], delta = t1 - t0;
+        const double* y0 = H->y + (size_t)(indx - 1) * ns;
+        const double* yd0 = H->yd + (size_t)(indx - 1) * ns;
+        if (newpoint) {
+            const double* y1 = H->y + (size_t)indx * ns;
+            const double* yd1 = H->yd + (size_t)indx * ns;
+            for (int k = 0; k < ns; ++k) {
+                H->Y1h[k] = -2.0 * y1[k] + 2.0 * y0[k] + delta * yd1[k] + delta * yd0[k];
+                H->Y0h[k] = y1[k] - y0[k] - delta * yd0[k];
+            }
+        }
+        double factor1 = t - t0;
+        double factor2 = factor1 / delta;
+        factor2 = factor2 * factor2;
+        double factor3 = factor2 * (t - t1) / delta;
+        for (int k = 0; k < ns; ++k)
+            y[k] = y0[k] + factor1 * yd0[k] + factor2 * H->Y0h[k] + factor3 * H->Y1h[k];
+        return 0;
+    }
 
     double delt = fabs(H->t[indx] - H->t[indx - 1]);
     int base, order;
@@ -1045,6 +1075,7 @@ typedef struct {
     const double* atol; int n_atol;       /* scalar (n_atol == 1) or per state */
     double rtol_b, atol_b, rtol_q, atol_q;
     int mxstep, max_retries, mxstep_b, max_retries_b;
+    int hermite;                          /* AdjointSolver(interpolation='hermite') */
 } oracle_options;
 
 static void set_fwd_tols(cv_mem* m, const oracle_options* o) {
@@ -1093,15 +1124,17 @@ static int adjoint_forward(const oracle_problem* prob, const oracle_options* opt
     set_fwd_tols(&m, opt);
     m.mxstep = opt->mxstep;
     cv_reinit(&m, t0, y0);
-    H->np = 0; H->ns = prob->ns; H->newdata = 1;
+    H->np = 0; H->ns = prob->ns; H->newdata = 1; H->hermite = opt->hermite;
     int first = 1, status = 0;
-    double tret = t0, ybuf[NMAX];
+    double tret = t0, ybuf[NMAX], ydbuf[NMAX];
     for (int i = 0; i < n_t && !status; ++i) {
         double tout = tvals[i];
         if (tout == t0) { memcpy(y_out, y0, sizeof(double) * m.N); continue; }
         /* CVodeF */
         if (first) {
-            if (hist_store(H, 0, m.tn, m.zn[0], m.qu)) return -20;
+            /* CVAhermiteStorePnt: y' of the initial point is f(t0, y0), later ones zn[1] / h */
+            if (H->hermite && prob->rhs(m.tn, m.zn[0], p, ydbuf)) return CV_FIRST_RHSFUNC_ERR;
+            if (hist_store(H, 0, m.tn, m.zn[0], m.qu, ydbuf)) return -20;
             first = 0;
         } else if ((m.tn - tout) * m.h >= 0.0) {
             if (cv_get_dky(&m, tout, ybuf)) { status = CV_BAD_T; break; }
@@ -1111,7 +1144,8 @@ static int adjoint_forward(const oracle_problem* prob, const oracle_options* opt
         for (;;) {
             int r = cv_solve(&m, tout, ybuf, &tret, CV_ONE_STEP);
             if (r < 0) { status = r; break; }
-            if (hist_store(H, m.nst, m.tn, m.zn[0], m.qu)) return -20;
+            if (H->hermite) for (int j = 0; j < m.N; ++j) ydbuf[j] = m.zn[1][j] / m.h;
+            if (hist_store(H, m.nst, m.tn, m.zn[0], m.qu, ydbuf)) return -20;
             if ((tret - tout) * m.h >= 0.0) {
                 (void)cv_get_dky(&m, tout, ybuf);
                 m.tretlast = tout;
@@ -1183,7 +1217,7 @@ static int adjoint_backward(const oracle_problem* prob, const oracle_options* op
     return status;
 }
 
-static void hist_free(hist_t* H) { free(H->t); free(H->y); free(H->order); }
+static void hist_free(hist_t* H) { free(H->t); free(H->y); free(H->yd); free(H->order); }
 
 /* ---- forward sensitivities: Solver(sens_mode=...).solve (solver.py:467-527 with 483-488, 523-527)
  * y_out[n_t][ns], sens_out[n_t][nd][ns]; sens0[nd][ns]. */

@@ -39,7 +39,8 @@ class _Options(ctypes.Structure):
                 ('rtol_b', ctypes.c_double), ('atol_b', ctypes.c_double),
                 ('rtol_q', ctypes.c_double), ('atol_q', ctypes.c_double),
                 ('mxstep', ctypes.c_int), ('max_retries', ctypes.c_int),
-                ('mxstep_b', ctypes.c_int), ('max_retries_b', ctypes.c_int)]
+                ('mxstep_b', ctypes.c_int), ('max_retries_b', ctypes.c_int),
+                ('hermite', ctypes.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -76,7 +77,8 @@ class Oracle:
 
     def __init__(self, problem=None, *, host_lib=None, sizes: Optional[Tuple[int, int, int]] = None,
                  rtol=1e-10, atol=1e-10, rtol_b=1e-10, atol_b=1e-10, rtol_q=1e-10, atol_q=1e-10,
-                 mxstep=500, max_retries=5, mxstep_b=500, max_retries_b=50, prefix='sbh_'):
+                 mxstep=500, max_retries=5, mxstep_b=500, max_retries_b=50, prefix='sbh_',
+                 interpolation='polynomial'):
         if problem is not None:
             host = problem.host_functions
             self._host = host
@@ -98,7 +100,8 @@ class Oracle:
             raise ValueError('atol must be a scalar or have one entry per state')
         self._atol = atol_arr
         self._opt = _Options(float(rtol), _dp(atol_arr), int(atol_arr.size), rtol_b, atol_b,
-                             rtol_q, atol_q, mxstep, max_retries, mxstep_b, max_retries_b)
+                             rtol_q, atol_q, mxstep, max_retries, mxstep_b, max_retries_b,
+                             int(interpolation == 'hermite'))
 
     # ------------------------------------------------------------------ helpers
     def _prep(self, y0, params, B=None):

@@ -35,20 +35,23 @@ def kernel_source_hash() -> str:
         for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh'):
             with open(os.path.join(_build.CSRC, name), 'rb') as fh:
                 h.update(fh.read())
+        # the compiler is part of the key: NVRTC versions generate different code
+        h.update(('nvrtc ' + _lib.nvrtc_version()).encode())
         _kernel_hash = h.hexdigest()[:16]
     return _kernel_hash
 
 
 def compile_cubin(gen: GeneratedSource, *, arch: str = DEFAULT_ARCH,
                   block_threads: Optional[int] = None, min_blocks: Optional[int] = None,
-                  use_cache: bool = True) -> Tuple[bytes, str]:
+                  use_cache: bool = True, defines: Tuple[str, ...] = ()) -> Tuple[bytes, str]:
     """JIT-compile (NVRTC, no GPU needed) the problem + integrator kernels; returns
     ``(cubin, path)``.  Results are cached in-tree keyed by problem, kernel sources and launch
-    configuration."""
+    configuration.  ``defines`` are build options of the kernels that a solver option selects
+    (``SB_HERMITE``, ``SB_CONSTRAINTS``); the default build defines none."""
     block = int(block_threads or DEFAULT_BLOCK)
     minb = int(min_blocks or DEFAULT_MIN_BLOCKS)
     # kernel build variants for A/B measurements: SUNODE_B200_DEFINES="SB_INLINE_MATH,SB_FOO=2"
-    defines = [d.strip() for d in os.environ.get('SUNODE_B200_DEFINES', '').split(',') if d.strip()]
+    defines = list(defines) + [d.strip() for d in os.environ.get('SUNODE_B200_DEFINES', '').split(',') if d.strip()]
     prelude = ''.join('#define %s\n' % d.replace('=', ' ', 1) for d in defines)
     tag = ('_' + hashlib.sha256(prelude.encode()).hexdigest()[:8]) if prelude else ''
     path = os.path.join(cache_dir(), 'k_%s_%s_%s_b%d_m%d%s.cubin'
@@ -140,14 +143,15 @@ class Engine:
 
     def __init__(self, gen: GeneratedSource, *, device: Optional[int] = None,
                  block_threads: Optional[int] = None, min_blocks: Optional[int] = None,
-                 arch: str = DEFAULT_ARCH):
+                 arch: str = DEFAULT_ARCH, defines: Tuple[str, ...] = ()):
         self.gen = gen
+        self.defines = tuple(defines)
         self.ns, self.np, self.nd = gen.n_states, gen.n_params, gen.n_deriv
         if device is None:
             device = int(os.environ.get('SUNODE_B200_DEVICE', os.environ.get('LOCAL_RANK', '0')))
         self.device = int(device)
         cubin, self.cubin_path = compile_cubin(gen, arch=arch, block_threads=block_threads,
-                                               min_blocks=min_blocks)
+                                               min_blocks=min_blocks, defines=self.defines)
         self._lib = _lib.lib()
         handle = ctypes.c_void_p()
         _lib.check(self._lib.sb_problem_create(ctypes.byref(handle), self.ns, self.np, self.nd,

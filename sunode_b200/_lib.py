@@ -45,6 +45,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         'sb_version': (c_int, []),
         'sb_last_error': (ctypes.c_char_p, []),
         'sb_device_count': (c_int, [ctypes.POINTER(c_int)]),
+        'sb_nvrtc_version': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
         'sb_compile': (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int,
                                ctypes.POINTER(_VP), ctypes.POINTER(c_size),
                                ctypes.POINTER(ctypes.c_void_p)]),
@@ -81,7 +82,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 EXPORTS = (
-    'sb_version', 'sb_last_error', 'sb_device_count', 'sb_compile', 'sb_free',
+    'sb_version', 'sb_last_error', 'sb_device_count', 'sb_nvrtc_version', 'sb_compile', 'sb_free',
     'sb_problem_create', 'sb_problem_destroy', 'sb_set_tolerances', 'sb_set_tolerances_b',
     'sb_set_quad_tolerances_b', 'sb_set_max_num_steps', 'sb_set_max_num_steps_b',
     'sb_set_history_capacity', 'sb_set_backward_trace', 'sb_solve_forward', 'sb_solve_forward_sens', 'sb_solve_backward',
@@ -122,6 +123,12 @@ def check(code: int) -> None:
     if code == SB_ERR_CUDA:
         raise DeviceError('sunode_b200: %s' % msg)
     raise LibraryError('sunode_b200 error %d: %s' % (code, msg))
+
+
+def nvrtc_version() -> str:
+    major, minor = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib().sb_nvrtc_version(ctypes.byref(major), ctypes.byref(minor)))
+    return '%d.%d' % (major.value, minor.value)
 
 
 def device_count() -> int:

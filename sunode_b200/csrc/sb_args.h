@@ -6,7 +6,7 @@
 #define SB_STATS_STRIDE 8     /* ints per instance: nst nfe nje nsetups netf ncfn nni aux */
 #define SB_CARRY_INTS 10      /* status, table index, 7 counters, pad */
 
-/* history point: (t, order, y[NS])                         -> NS + 2 doubles
+/* history point: (t, order, y[NS]) (+ y'[NS] with SB_HERMITE) -> NS + 2 (2 NS + 2) doubles
  * interpolation table entry for the interval (t_lo, t_hi):
  *   [0] t_lo [1] t_hi [2] order [3] 1/delt [4..9] T[0..5] [10 + NS*j + k] Y[j][k]  -> 10 + 6*NS */
 /* Lanes of a warp that integrate one instance together (sb_group.cuh): one for small systems, from
@@ -23,7 +23,15 @@
 #define SB_GROUP_SIZE(ns) ((ns) < SB_GROUP_MIN_NS ? 1 : (ns) <= 4 ? 2 : (ns) <= 8 ? 4 : (ns) <= 16 ? 8 : (ns) <= 32 ? 16 : (ns) <= 64 ? 32 : 1)
 #endif
 
+/* -DSB_HERMITE (AdjointSolver(interpolation='hermite'), CV_HERMITE of
+ * /root/reference/sunode/solver.py:581-586): every history point also carries y' = zn[1] / h, and
+ * the table entry of an interval is the cubic through (y, y') at its two ends, written in the same
+ * Newton form (order 3, nodes t_hi, t_hi, t_lo) -- the backward kernels do not change. */
+#ifdef SB_HERMITE
+#define SB_HIST_STRIDE(ns) (2 * (ns) + 2)
+#else
 #define SB_HIST_STRIDE(ns) ((ns) + 2)
+#endif
 #define SB_TAB_STRIDE(ns) (10 + 6 * (ns))
 
 typedef struct SbForwardArgs {

@@ -86,6 +86,31 @@ using FwdSys = FwdSysT<1>;
 // the right end point.  `hist` / `tab` are this instance's arrays.
 __device__ __forceinline__ void build_table_entry_at(const double* hist, double* tab, int idx) {
     double* e = tab + (size_t)idx * TAB_STRIDE;
+#ifdef SB_HERMITE
+    // CVAhermiteGetY: the cubic through (y, y') at both ends of the interval, as a Newton form
+    // with the nodes t_hi, t_hi, t_lo (scaled by powers of the interval length like the
+    // polynomial entries, so the backward kernels evaluate it unchanged as an order-3 entry)
+    {
+        const double* p1 = hist + (size_t)idx * HIST_STRIDE;
+        const double* p0 = p1 - HIST_STRIDE;
+        const double t1 = p1[0], t0 = p0[0];
+        const double D = t1 - t0, a = fabs(D);
+        const double sgn = (D >= 0.0) ? 1.0 : -1.0;       // a / D
+        e[0] = t0; e[1] = t1; e[2] = 3.0; e[3] = 1.0 / a;
+        e[4] = t1; e[5] = t1; e[6] = t0; e[7] = 0.0; e[8] = 0.0; e[9] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const double y1 = p1[2 + k], y0 = p0[2 + k], yd1 = p1[2 + NS + k], yd0 = p0[2 + NS + k];
+            const double dy = y1 - y0;
+            e[10 + k] = y1;
+            e[10 + NS + k] = a * yd1;
+            e[10 + 2 * NS + k] = sgn * (a * yd1 - sgn * dy);
+            e[10 + 3 * NS + k] = a * (yd1 + yd0) - 2.0 * sgn * dy;
+            e[10 + 4 * NS + k] = 0.0;
+            e[10 + 5 * NS + k] = 0.0;
+        }
+    }
+#else
     int order = (int)hist[(size_t)idx * HIST_STRIDE + 1];
     if (order > idx) order = idx;
     if (order < 1) order = 1;
@@ -125,14 +150,21 @@ __device__ __forceinline__ void build_table_entry_at(const double* hist, double*
     for (int j = 0; j < SB_LMAX; ++j)
 #pragma unroll
         for (int k = 0; k < NS; ++k) e[10 + NS * j + k] = Y[j][k];
+#endif
 }
 
-__device__ __forceinline__ void store_point(double* hist, int idx, double t, int order, const double* y) {
+// `hyd` = zn[1] = h y' of the step that ended at t (CVAhermiteStorePnt keeps zn[1] / h)
+__device__ __forceinline__ void store_point(double* hist, int idx, double t, int order, const double* y,
+                                            const double* hyd, double h) {
     double* e = hist + (size_t)idx * HIST_STRIDE;
     e[0] = t;
     e[1] = (double)order;
 #pragma unroll
     for (int i = 0; i < NS; ++i) e[2 + i] = y[i];
+#ifdef SB_HERMITE
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[2 + NS + i] = hyd[i] / h;
+#endif
 }
 
 // Warp-synchronous driver.  ptxas does not re-converge the lanes of a warp after loops whose trip
@@ -211,7 +243,7 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
             // what CVode() does before it calls cvStep
             if (bdf.nst == 0) {
                 status = bdf.first_call(sys, a.tvals[k]);
-                if (status == SB_SUCCESS && hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0]);
+                if (status == SB_SUCCESS && hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0], bdf.zn[1], bdf.h);
             }
             if (status == SB_SUCCESS) {
                 if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
@@ -227,7 +259,7 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
             if (r == SB_SUCCESS) {
                 nloc++;
                 if (hist) {
-                    store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0]);
+                    store_point(hist, bdf.nst, bdf.tn, bdf.qu, bdf.zn[0], bdf.zn[1], bdf.h);
                     if (tab) build_table_entry_at(hist, tab, bdf.nst);
                 }
             } else if (r != SB_TRY_AGAIN) {
@@ -648,6 +680,7 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
 
 // read by the launcher (instances per warp of the backward kernels = 32 / sb_group_size)
 __device__ int sb_group_size = sb::GROUP;
+__device__ int sb_hist_stride = sb::HIST_STRIDE;   // doubles per history point (the launcher sizes the buffer)
 
 extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {

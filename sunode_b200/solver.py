@@ -347,15 +347,17 @@ class AdjointSolver(_ParamsMixin):
             raise NotImplementedError('Only the BDF method is implemented on the B200 engine.')
         if interpolation not in ('polynomial', 'hermite'):
             assert False
-        if interpolation != 'polynomial':
-            raise NotImplementedError('Only polynomial interpolation of the forward solution is implemented.')
         if constraints is not None:
             raise NotImplementedError('Constraints are not implemented.')
         self._problem = problem
         self._user_data = problem.make_user_data()
         self._constraints = constraints
+        self._interpolation = interpolation
+        # CV_HERMITE (solver.py:581-586): the forward kernel also stores y' at every step and the
+        # table kernel writes cubic Hermite entries; a build option of the kernels (csrc/sb_args.h)
+        defines = ('SB_HERMITE',) if interpolation == 'hermite' else ()
         self._engine = Engine(problem.generated, device=device, block_threads=block_threads,
-                              min_blocks=min_blocks)
+                              min_blocks=min_blocks, defines=defines)
         # the reference keeps every forward step of one solve in memory (checkpoint_n = 500 000
         # steps per checkpoint, solver.py:533,588); here the per-instance capacity is explicit
         self._history_capacity = int(history_capacity or min(int(checkpoint_n), 1024))

@@ -63,6 +63,7 @@ class Emulator:
             defines = tuple(defines) + ('SB_HOST_EMULATION_GROUP',)
         gen = problem.generated
         self.ns, self.np, self.nd = gen.n_states, gen.n_params, gen.n_deriv
+        self.hist_stride = (2 * self.ns + 2) if 'SB_HERMITE' in defines else self.ns + 2
         os.makedirs(workdir, exist_ok=True)
         inc = os.path.join(workdir, 'generated_problem.inc')
         with open(inc, 'w') as fh:
@@ -96,7 +97,7 @@ class Emulator:
         y_out = np.zeros((B, n_t, self.ns))
         status = np.zeros(B, dtype=np.int32)
         stats = np.zeros((B, STATS), dtype=np.int32)
-        hist = np.zeros((B, hist_cap, self.ns + 2)) if hist_cap else None
+        hist = np.zeros((B, hist_cap, self.hist_stride)) if hist_cap else None
         hist_n = np.zeros(B, dtype=np.int32)
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,

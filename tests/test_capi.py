@@ -41,9 +41,12 @@ def test_header_is_plain_c():
                         os.path.join(ROOT, 'include'), '-o', os.path.join(tmp, 'hdr.o')], check=True)
 
 
-def test_compile_for_sm100a_without_gpu():
+def test_compile_for_sm100a_without_gpu(tmp_path, monkeypatch):
+    # a scratch cache: this compile must not replace the cubin build() put into the tree
+    monkeypatch.setenv('SUNODE_B200_CACHE', str(tmp_path))
     gen = examples.lotka_volterra().generated
     cubin, path = _engine.compile_cubin(gen, use_cache=False)
+    assert os.path.dirname(path) == str(tmp_path)
     assert cubin[:4] == b'\x7fELF' and os.path.exists(path)
     import subprocess
     out = subprocess.run(['cuobjdump', '-elf', path], capture_output=True, text=True).stdout
