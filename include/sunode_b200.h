@@ -69,6 +69,10 @@ int sb_problem_destroy(sb_problem* p);
 
 /* CVodeSStolerances / CVodeSVtolerances (solver.py:394-417, 624-635). n_atol is 1 or n_states. */
 int sb_set_tolerances(sb_problem* p, double rtol, const double* atol, int n_atol);
+/* CVodeSetSensParams(ode, NULL, pbar, NULL) (solver.py:381-387, `scaling_factors`): with
+ * CVodeSensEEtolerances (solver.py:389) the sensitivity block k is integrated with the absolute
+ * tolerance atol / |pbar[k]|.  n = n_deriv; pbar = NULL restores pbar = 1. */
+int sb_set_sens_scaling(sb_problem* p, const double* pbar, int n);
 /* CVodeSStolerancesB (solver.py:599; README.md:246) */
 int sb_set_tolerances_b(sb_problem* p, double rtol, double atol);
 /* CVodeQuadSStolerancesB (solver.py:614; README.md:247) */

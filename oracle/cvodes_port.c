@@ -54,6 +54,7 @@
 #define CV_FIRST_RHSFUNC_ERR (-9)
 #define CV_REPTD_RHSFUNC_ERR (-10)
 #define CV_UNREC_RHSFUNC_ERR (-11)
+#define CV_CONSTR_FAIL (-15)
 #define CV_ILL_INPUT (-22)
 #define CV_BAD_T (-25)
 #define CV_TOO_CLOSE (-27)
@@ -105,6 +106,7 @@
 #define TRY_AGAIN 5
 #define CONV_FAIL 4
 #define RHSFUNC_RECVR 9
+#define CONSTR_RECVR 10
 #define QRHSFUNC_RECVR 11
 #define NO_FAILURES 0
 #define FAIL_BAD_J 1
@@ -162,6 +164,7 @@ typedef struct cv_mem {
     const oracle_problem* prob;
     const double* p;
     hist_t* hist;            /* backward problems interpolate the forward solution from here */
+    const double* constraints;   /* CVodeSetConstraints flags per component (0, +-1, +-2) or NULL */
 
     double reltol, abstol[NMAX];
     double reltolQ, abstolQ;
@@ -513,6 +516,8 @@ static int ls_setup(cv_mem* m, int convfail, const double* ypred) {
 }
 
 /* ---- nonlinear solve (cvNls + SUNNonlinSol_Newton + cvNlsConvTest) ---------------------------- */
+static int cv_check_constraints(cv_mem* m);
+
 static int cv_nls(cv_mem* m, int nflag) {
     int n = m->N;
     int callSetup;
@@ -559,6 +564,7 @@ static int cv_nls(cv_mem* m, int nflag) {
                 m->acnrm = (curiter == 0) ? del : vnorm(m, m->acor, m->ewt);
                 m->jcur = 0;
                 for (int i = 0; i < n; ++i) m->y[i] = m->zn[0][i] + m->acor[i];
+                if (m->constraints) return cv_check_constraints(m);
                 return CV_SUCCESS;
             }
             if (!(dcon <= 1.0) && !(dcon > 1.0)) { retval = CONV_FAIL; break; }   /* NaN guard */
@@ -587,6 +593,40 @@ done:
     return retval;
 }
 
+/* N_VConstrMask for one component: does x violate its constraint flag c? */
+static int constr_violated(double c, double x) {
+    if (fabs(c) > 1.5) return x * c <= 0.0;
+    if (fabs(c) > 0.5) return x * c < 0.0;
+    return 0;
+}
+
+/* cvCheckConstraints (called at the end of cvNls after a converged solve): a violation whose
+ * correction v is small (||v|| <= tq[4]) is projected away by changing acor; otherwise eta is set
+ * for a smaller step and CONSTR_RECVR returned. */
+static int cv_check_constraints(cv_mem* m) {
+    int n = m->N, any = 0;
+    double* mm = m->ftemp; double* tmp = m->tempv;
+    for (int i = 0; i < n; ++i) { mm[i] = constr_violated(m->constraints[i], m->y[i]) ? 1.0 : 0.0; any |= (mm[i] != 0.0); }
+    if (!any) return CV_SUCCESS;
+    for (int i = 0; i < n; ++i) {
+        double a = (fabs(m->constraints[i]) >= 1.5) ? 1.0 : 0.0;
+        tmp[i] = mm[i] * (m->y[i] - 0.1 * (a * m->constraints[i] / m->ewt[i]));
+    }
+    double vnorm = wrms(tmp, m->ewt, n);
+    if (vnorm <= m->tq[4]) {
+        for (int i = 0; i < n; ++i) m->acor[i] -= tmp[i];
+        return CV_SUCCESS;
+    }
+    if (fabs(m->h) <= m->hmin * ONEPSM) return CV_CONSTR_FAIL;
+    double mq = DBL_MAX;
+    for (int i = 0; i < n; ++i) {
+        double d = mm[i] * (m->zn[0][i] - m->y[i]);
+        if (d != 0.0) mq = fmin(mq, m->zn[0][i] / d);
+    }
+    m->eta = fmax(0.9 * mq, 0.1);
+    return CONSTR_RECVR;
+}
+
 static int cv_handle_nflag(cv_mem* m, int* nflagPtr, double saved_t, int* ncfPtr, long* ncfnPtr) {
     int nflag = *nflagPtr;
     if (nflag == CV_SUCCESS) return DO_ERROR_TEST;
@@ -597,9 +637,11 @@ static int cv_handle_nflag(cv_mem* m, int* nflagPtr, double saved_t, int* ncfPtr
     m->etamax = 1.0;
     if (fabs(m->h) <= m->hmin * ONEPSM || *ncfPtr == MXNCF) {
         if (nflag == CONV_FAIL) return CV_CONV_FAILURE;
+        if (nflag == CONSTR_RECVR) return CV_CONSTR_FAIL;
         return CV_REPTD_RHSFUNC_ERR;
     }
-    m->eta = fmax(ETACF, m->hmin / fabs(m->h));
+    /* for CONSTR_RECVR eta was already set by cv_check_constraints */
+    if (nflag != CONSTR_RECVR) m->eta = fmax(ETACF, m->hmin / fabs(m->h));
     *nflagPtr = PREV_CONV_FAIL;
     cv_rescale(m);
     return PREDICT_AGAIN;
@@ -800,6 +842,10 @@ static int cv_solve(cv_mem* m, double tout, double* yout, double* tret, int itas
 
     if (m->nst == 0) {
         m->tretlast = *tret = m->tn;
+        /* cvInitialSetup: y0 must satisfy the constraints */
+        if (m->constraints)
+            for (int i = 0; i < m->N; ++i)
+                if (constr_violated(m->constraints[i], m->zn[0][i])) return CV_ILL_INPUT;
         if (ewt_set(m, m->zn[0], m->ewt)) return CV_ILL_INPUT;
         if (m->quadr && m->errconQ && ewtQ_set(m, m->znQ[0], m->ewtQ)) return CV_ILL_INPUT;
         int r = m->f(m, m->tn, m->zn[0], m->zn[1]); m->nfe++;
@@ -1076,11 +1122,17 @@ typedef struct {
     double rtol_b, atol_b, rtol_q, atol_q;
     int mxstep, max_retries, mxstep_b, max_retries_b;
     int hermite;                          /* AdjointSolver(interpolation='hermite') */
+    const double* constraints;            /* [ns] CVodeSetConstraints flags of the forward ODE, or NULL */
+    const double* pbar;                   /* [nd] CVodeSetSensParams scaling factors, or NULL (= 1) */
 } oracle_options;
 
 static void set_fwd_tols(cv_mem* m, const oracle_options* o) {
     m->reltol = o->rtol;
-    for (int i = 0; i < m->N; ++i) m->abstol[i] = (o->n_atol == 1) ? o->atol[0] : o->atol[i % m->NM];
+    for (int i = 0; i < m->N; ++i) {
+        m->abstol[i] = (o->n_atol == 1) ? o->atol[0] : o->atol[i % m->NM];
+        /* cvSensEwtSetEE: ewtS = pbar / (rtol |pbar yS| + atol), i.e. atolS = atol / |pbar| */
+        if (o->pbar && i >= m->NM) m->abstol[i] /= fabs(o->pbar[i / m->NM - 1]);
+    }
 }
 
 /* stats layout: nst, nfe, nje, nsetups, netf, ncfn, nni, (bwd) nst, nfe, nje, nsetups, netf(+Q), ncfn, nni */
@@ -1095,6 +1147,7 @@ int oracle_solve_forward(const oracle_problem* prob, const oracle_options* opt,
     m.N = prob->ns; m.NM = prob->ns; m.nblk = 1; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
     set_fwd_tols(&m, opt);
     m.mxstep = opt->mxstep;
+    m.constraints = opt->constraints;
     cv_reinit(&m, t0, y0);
     int status = 0;
     double tret = t0, ybuf[NMAX];
@@ -1123,6 +1176,7 @@ static int adjoint_forward(const oracle_problem* prob, const oracle_options* opt
     m.N = prob->ns; m.NM = prob->ns; m.nblk = 1; m.NQ = 0; m.f = fwd_rhs; m.jacfn = fwd_jac; m.prob = prob; m.p = p;
     set_fwd_tols(&m, opt);
     m.mxstep = opt->mxstep;
+    m.constraints = opt->constraints;
     cv_reinit(&m, t0, y0);
     H->np = 0; H->ns = prob->ns; H->newdata = 1; H->hermite = opt->hermite;
     int first = 1, status = 0;

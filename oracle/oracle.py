@@ -40,7 +40,7 @@ class _Options(ctypes.Structure):
                 ('rtol_q', ctypes.c_double), ('atol_q', ctypes.c_double),
                 ('mxstep', ctypes.c_int), ('max_retries', ctypes.c_int),
                 ('mxstep_b', ctypes.c_int), ('max_retries_b', ctypes.c_int),
-                ('hermite', ctypes.c_int)]
+                ('hermite', ctypes.c_int), ('constraints', _DP), ('pbar', _DP)]
 
 
 def build(force: bool = False) -> str:
@@ -78,7 +78,7 @@ class Oracle:
     def __init__(self, problem=None, *, host_lib=None, sizes: Optional[Tuple[int, int, int]] = None,
                  rtol=1e-10, atol=1e-10, rtol_b=1e-10, atol_b=1e-10, rtol_q=1e-10, atol_q=1e-10,
                  mxstep=500, max_retries=5, mxstep_b=500, max_retries_b=50, prefix='sbh_',
-                 interpolation='polynomial'):
+                 interpolation='polynomial', constraints=None, scaling_factors=None):
         if problem is not None:
             host = problem.host_functions
             self._host = host
@@ -101,7 +101,15 @@ class Oracle:
         self._atol = atol_arr
         self._opt = _Options(float(rtol), _dp(atol_arr), int(atol_arr.size), rtol_b, atol_b,
                              rtol_q, atol_q, mxstep, max_retries, mxstep_b, max_retries_b,
-                             int(interpolation == 'hermite'))
+                             int(interpolation == 'hermite'), None, None)
+        if scaling_factors is not None:
+            self._pbar = np.ascontiguousarray(scaling_factors, dtype=np.float64)
+            assert self._pbar.shape == (nd,)
+            self._opt.pbar = _dp(self._pbar)
+        if constraints is not None:
+            self._constraints = np.ascontiguousarray(
+                np.broadcast_to(np.asarray(constraints, dtype=np.float64), (ns,)))
+            self._opt.constraints = _dp(self._constraints)
 
     # ------------------------------------------------------------------ helpers
     def _prep(self, y0, params, B=None):

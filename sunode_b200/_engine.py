@@ -169,6 +169,14 @@ class Engine:
             self._h, float(rtol), atol.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             int(atol.size)))
 
+    def set_sens_scaling(self, pbar) -> None:
+        if pbar is None:
+            _lib.check(self._lib.sb_set_sens_scaling(self._h, None, 0))
+            return
+        pbar = np.ascontiguousarray(pbar, dtype=np.float64)
+        _lib.check(self._lib.sb_set_sens_scaling(
+            self._h, pbar.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(pbar.size)))
+
     def set_tolerances_b(self, rtol: float, atol: float) -> None:
         _lib.check(self._lib.sb_set_tolerances_b(self._h, float(rtol), float(atol)))
 

@@ -54,6 +54,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         'sb_problem_destroy': (c_int, [_VP]),
         'sb_set_tolerances': (c_int, [_VP, c_double, _DP, c_int]),
         'sb_set_tolerances_b': (c_int, [_VP, c_double, c_double]),
+        'sb_set_sens_scaling': (c_int, [_VP, ctypes.POINTER(c_double), c_int]),
         'sb_set_quad_tolerances_b': (c_int, [_VP, c_double, c_double]),
         'sb_set_max_num_steps': (c_int, [_VP, c_int, c_int]),
         'sb_set_max_num_steps_b': (c_int, [_VP, c_int, c_int]),
@@ -84,7 +85,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 EXPORTS = (
     'sb_version', 'sb_last_error', 'sb_device_count', 'sb_nvrtc_version', 'sb_compile', 'sb_free',
     'sb_problem_create', 'sb_problem_destroy', 'sb_set_tolerances', 'sb_set_tolerances_b',
-    'sb_set_quad_tolerances_b', 'sb_set_max_num_steps', 'sb_set_max_num_steps_b',
+    'sb_set_sens_scaling', 'sb_set_quad_tolerances_b', 'sb_set_max_num_steps', 'sb_set_max_num_steps_b',
     'sb_set_history_capacity', 'sb_set_backward_trace', 'sb_solve_forward', 'sb_solve_forward_sens', 'sb_solve_backward',
     'sb_solve_adjoint',
     'sb_eval', 'sb_synchronize', 'sb_last_kernel_ms', 'sb_launch_count', 'sb_kernel_info',

@@ -30,6 +30,7 @@ CV_RHSFUNC_FAIL = -8
 CV_FIRST_RHSFUNC_ERR = -9
 CV_REPTD_RHSFUNC_ERR = -10
 CV_UNREC_RHSFUNC_ERR = -11
+CV_CONSTR_FAIL = -15
 CV_MEM_FAIL = -20
 CV_MEM_NULL = -21
 CV_ILL_INPUT = -22

@@ -40,7 +40,7 @@ typedef struct SbForwardArgs {
     const double* tvals;      /* [n_t] */
     const double* y0;         /* [B][NS] */
     const double* params;     /* [B][NP] */
-    const double* atol;       /* [NS] */
+    const double* atol;       /* [NS * (1 + ND)]: states, then the sensitivity blocks (atol / |pbar_k|) */
     double* y_out;            /* [B][n_t][NS] */
     double* hist;             /* [B][hist_cap][NS+2] or NULL */
     int* hist_n;              /* [B] number of stored points */

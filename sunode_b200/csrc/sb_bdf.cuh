@@ -37,12 +37,19 @@
 #define SB_REPTD_RHSFUNC_ERR (-10)
 #define SB_UNREC_RHSFUNC_ERR (-11)
 #define SB_ILL_INPUT (-22)
+#define SB_CONSTR_FAIL (-15)
 #define SB_BAD_T (-25)
 #define SB_TOO_CLOSE (-27)
 #define SB_GETY_BADT (-107)
 #define SB_TRY_AGAIN 5          /* internal: attempt() wants another pass */
 
 namespace sb {
+
+#ifdef SB_CONSTRAINTS
+// Solver(constraints=...) / AdjointSolver(constraints=...): one flag per state, a build option
+// of the kernels (-DSB_CONSTRAINTS=c_0,c_1,...); see Bdf::check_constraints
+__device__ constexpr double sb_constraints[SB_NS] = {SB_CONSTRAINTS};
+#endif
 
 constexpr double ETAMX1 = 10000.0, ETAMX2 = 10.0, ETAMX3 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1;
 constexpr double ETACF = 0.25, ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
@@ -528,7 +535,7 @@ struct Bdf {
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double d = fma(sys.rtol(), fabs(zn[0][i]), sys.atol(i % NM));
+            const double d = fma(sys.rtol(), fabs(zn[0][i]), sys.atol(i));   // per stacked component
             ok = ok && (d > 0.0);
             ewt[i] = sb_div(1.0, d);
         }
@@ -1149,6 +1156,52 @@ struct Bdf {
         return 0;
     }
 
+#ifdef SB_CONSTRAINTS
+    // ------------------------------------------------------------------ inequality constraints
+    // CVodeSetConstraints (/root/reference/sunode/solver.py:268-271, 568-572): SB_CONSTRAINTS is
+    // the list of per-component flags, 0 none, +-1 y >= 0 / <= 0, +-2 y > 0 / < 0.
+    // N_VConstrMask: is component i of y in violation?
+    __device__ static __forceinline__ bool constr_violated(int i, double y) {
+        const double c = sb_constraints[i];
+        return (fabs(c) > 1.5) ? (y * c <= 0.0) : (fabs(c) > 0.5) ? (y * c < 0.0) : false;
+    }
+    __device__ __forceinline__ bool constraints_hold(const double* y) const {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < NM; ++i) ok = ok && !constr_violated(i, y[i]);
+        return ok;
+    }
+    // cvCheckConstraints on the converged iterate ycur = zn[0] + acor.  A small violation is
+    // projected away (acor -= v) and the step goes on to the error test; otherwise eta is set for
+    // a smaller step and true is returned.
+    __device__ __forceinline__ bool check_constraints() {
+        double v[N];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool m = i < NM && constr_violated(i, ycur[i]);
+            const double c = sb_constraints[i < NM ? i : 0];
+            const double ac = (i < NM && fabs(c) > 1.5) ? c : 0.0;      // a * c: the strict ones
+            v[i] = m ? ycur[i] - 0.1 * sb_div(ac, ewt[i]) : 0.0;
+            any = any || m;
+        }
+        if (!any) return false;
+        if (norm2(v) * tq[4] <= 1.0) {          // ||v|| <= CVODES' tq[4]
+#pragma unroll
+            for (int i = 0; i < N; ++i) acor[i] -= v[i];
+            return false;
+        }
+        double mq = 1.7976931348623157e308;     // N_VMinQuotient(zn[0], mm * (zn[0] - y))
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+            const double d = zn[0][i] - ycur[i];
+            if (constr_violated(i, ycur[i]) && d != 0.0) mq = fmin(mq, sb_div(zn[0][i], d));
+        }
+        eta = fmax(0.9 * mq, 0.1);
+        return true;
+    }
+#endif
+
     // ------------------------------------------------------------------ one internal step (cvStep)
     // One pass of cvStep's predict / solve / test loop, entered together by the lanes in `mask`.
     // Returns SB_SUCCESS when the step is complete, SB_TRY_AGAIN when the pass failed recoverably
@@ -1189,14 +1242,33 @@ struct Bdf {
                     result = SB_TRY_AGAIN;
                 }
             } else {
-                dsm2 = acnrm2 * tq[2];
-                if (!(dsm2 <= 1.0)) {
-                    nef++;
-                    nflag = PREV_ERR_FAIL;
-                    const int r = error_test_failed(dsm2, nef);
+#ifdef SB_CONSTRAINTS
+                bool cfail = false;
+                if constexpr (Sys::CONSTR) cfail = check_constraints();
+                if (cfail) {
+                    // CONSTR_RECVR in cvHandleNFlag: counted like a convergence failure, but the
+                    // step-size ratio is the one cvCheckConstraints chose
+                    st.ncfn++; ncf++;
+                    etamax = 1.0;
                     go = false;
-                    if (r < 0) { in_step = false; result = r; }
-                    else result = SB_TRY_AGAIN;
+                    if (ncf == MXNCF) { in_step = false; result = SB_CONSTR_FAIL; }
+                    else {
+                        nflag = PREV_CONV_FAIL;
+                        pend = PEND_RESTORE | PEND_RESCALE;
+                        result = SB_TRY_AGAIN;
+                    }
+                } else
+#endif
+                {
+                    dsm2 = acnrm2 * tq[2];
+                    if (!(dsm2 <= 1.0)) {
+                        nef++;
+                        nflag = PREV_ERR_FAIL;
+                        const int r = error_test_failed(dsm2, nef);
+                        go = false;
+                        if (r < 0) { in_step = false; result = r; }
+                        else result = SB_TRY_AGAIN;
+                    }
                 }
             }
         }

@@ -190,6 +190,9 @@ template <int G>
 struct BwdSysG {
     using LG = LaneGroup<G>;
     static constexpr bool TSTOP = true;
+#ifdef SB_CONSTRAINTS
+    static constexpr bool CONSTR = false;
+#endif
     static constexpr int GROUP = G, NS_FULL = NS, NQ_FULL = ND_;
     static constexpr bool MAT_SHARED = true;
     static constexpr int NQL = (ND + G - 1) / G > 0 ? (ND + G - 1) / G : 1;   // quadrature components per lane

@@ -56,6 +56,9 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000
 template <int NBLK>
 struct FwdSysT {
     static constexpr bool TSTOP = false;
+#ifdef SB_CONSTRAINTS
+    static constexpr bool CONSTR = (NBLK == 1);    // the reference constrains the forward ODE only
+#endif
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = 1;
     static constexpr bool MAT_SHARED = false;
     struct GroupIds {};
@@ -242,6 +245,11 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
         if (work && !bdf.in_step) {
             // what CVode() does before it calls cvStep
             if (bdf.nst == 0) {
+#ifdef SB_CONSTRAINTS
+                // cvInitialSetup: y0 must satisfy the constraints
+                if (Sys::CONSTR && !bdf.constraints_hold(y0)) status = SB_ILL_INPUT;
+                else
+#endif
                 status = bdf.first_call(sys, a.tvals[k]);
                 if (status == SB_SUCCESS && hist) store_point(hist, 0, bdf.tn, 0, bdf.zn[0], bdf.zn[1], bdf.h);
             }
@@ -312,6 +320,9 @@ __device__ __forceinline__ void build_table_entry(const SbTablesArgs& a, long lo
 // ------------------------------------------------------------------------------------ backward
 struct BwdSys {
     static constexpr bool TSTOP = true;
+#ifdef SB_CONSTRAINTS
+    static constexpr bool CONSTR = false;
+#endif
     static constexpr int GROUP = 1, NS_FULL = NS, NQ_FULL = ND_;
     // saved Jacobian + Newton matrix in shared memory (2..4 states; measured: LV backward 17.76 ->
     // 16.78 ms, the 16 registers end the spilling; Robertson 208 -> 193 ms).  From 5 states on the

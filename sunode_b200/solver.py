@@ -138,12 +138,28 @@ def _raise_forward(status: int, tvals, y_row) -> None:
     raise SolverError(f"Solving ode failed before time={t_fail}: {error} ({int(status)})")
 
 
+def _constraint_defines(constraints, n_states) -> Tuple[Optional[np.ndarray], Tuple[str, ...]]:
+    """``constraints`` of the reference (solver.py:268-271, 566-572: broadcast to the states and
+    handed to ``CVodeSetConstraints``; flags 0 none, +-1 ``y >= 0`` / ``<= 0``, +-2 strict) as a
+    build option of the kernels: the flags are compile-time constants of the forward integrator
+    (``Bdf::check_constraints`` in csrc/sb_bdf.cuh)."""
+    if constraints is None:
+        return None, ()
+    c = np.broadcast_to(np.asarray(constraints, dtype=np.float64), (n_states,)).copy()
+    if not np.isin(c, (-2.0, -1.0, 0.0, 1.0, 2.0)).all():
+        raise ValueError('Bad return code from sundials: CV_ILL_INPUT (-22)')   # CVodeSetConstraints
+    if not c.any():
+        return c, ()
+    return c, ('SB_CONSTRAINTS=' + ','.join('%.1f' % v for v in c),)
+
+
 class Solver(_ParamsMixin):
     """Forward solver (reference ``Solver``, solver.py:213-527), dense-BDF path.
 
     Options of the reference that select other SUNDIALS modules are accepted for signature
     compatibility and rejected with ``NotImplementedError`` when they would change the
-    algorithm (ADAMS, non-dense linear solvers, constraints).
+    algorithm (ADAMS, non-dense linear solvers).  ``constraints`` (CVodeSetConstraints flags per
+    state) are a build option of the forward kernel.
 
     ``sens_mode`` = ``"simultaneous"`` or ``"staggered"`` turns on forward sensitivity analysis
     (reference solver.py:360-392): y and dy/dp_k for the derivative parameters are integrated
@@ -176,10 +192,14 @@ class Solver(_ParamsMixin):
             scaling_factors = np.asarray(scaling_factors, dtype=np.float64)
             if scaling_factors.shape != (problem.n_params,):
                 raise ValueError('Invalid shape of scaling_factors.')
-            if not np.all(scaling_factors == 1.0):
-                raise NotImplementedError('scaling_factors other than 1 are not implemented.')
-        if constraints is not None:
-            raise NotImplementedError('Constraints are not implemented.')
+            if sens_mode is not None and not np.all(scaling_factors != 0.0):
+                # CVodeSetSensParams: "pbar has zero component(s) (illegal)"
+                raise ValueError('Bad return code from sundials: CV_ILL_INPUT (-22)')
+        constraints, self._defines = _constraint_defines(constraints, problem.n_states)
+        if self._defines and sens_mode is not None:
+            # CVODES rejects constraints together with the simultaneous corrector (the one the
+            # engine implements) at the first solve: CV_ILL_INPUT
+            raise NotImplementedError('Constraints together with forward sensitivities are not implemented.')
         self._problem = problem
         self._user_data = problem.make_user_data()
         self._constraints = constraints
@@ -188,19 +208,26 @@ class Solver(_ParamsMixin):
         self._linear_solver_kind = linear_solver
         self._linear_solver_kwargs = linear_solver_kwargs
         self._sens_mode = sens_mode
+        self._scaling_factors = scaling_factors
         self._solver_kind = solver
         self._device = device
         self._launch_cfg = (block_threads, min_blocks)
         self._mxstep = 500
         self._state_names = ['_problem', '_user_data', '_constraints', '_abstol', '_reltol',
                              '_linear_solver_kind', '_linear_solver_kwargs', '_sens_mode',
-                             '_solver_kind', '_device', '_launch_cfg', '_mxstep', '_state_names']
+                             '_scaling_factors',
+                             '_solver_kind', '_device', '_launch_cfg', '_mxstep', '_defines',
+                             '_state_names']
         self._init_engine()
 
     def _init_engine(self) -> None:
         self._compute_sens = self._sens_mode is not None
         self._engine = Engine(self._problem.generated, device=self._device,
-                              block_threads=self._launch_cfg[0], min_blocks=self._launch_cfg[1])
+                              block_threads=self._launch_cfg[0], min_blocks=self._launch_cfg[1],
+                              defines=self._defines)
+        if self._compute_sens and self._scaling_factors is not None:
+            # CVodeSetSensParams(pbar) + CVodeSensEEtolerances (solver.py:381-389)
+            self._engine.set_sens_scaling(self._scaling_factors)
         self._set_tolerances(self._abstol, self._reltol)
 
     # pickling like the reference (solver.py:319-324): configuration only, handle re-created
@@ -347,15 +374,14 @@ class AdjointSolver(_ParamsMixin):
             raise NotImplementedError('Only the BDF method is implemented on the B200 engine.')
         if interpolation not in ('polynomial', 'hermite'):
             assert False
-        if constraints is not None:
-            raise NotImplementedError('Constraints are not implemented.')
+        constraints, constraint_defines = _constraint_defines(constraints, problem.n_states)
         self._problem = problem
         self._user_data = problem.make_user_data()
         self._constraints = constraints
         self._interpolation = interpolation
         # CV_HERMITE (solver.py:581-586): the forward kernel also stores y' at every step and the
         # table kernel writes cubic Hermite entries; a build option of the kernels (csrc/sb_args.h)
-        defines = ('SB_HERMITE',) if interpolation == 'hermite' else ()
+        defines = (('SB_HERMITE',) if interpolation == 'hermite' else ()) + constraint_defines
         self._engine = Engine(problem.generated, device=device, block_threads=block_threads,
                               min_blocks=min_blocks, defines=defines)
         # the reference keeps every forward step of one solve in memory (checkpoint_n = 500 000

@@ -106,11 +106,14 @@ class Emulator:
         return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
                     params=params, tvals=tvals)
 
-    def forward_sens(self, t0, tvals, y0, params, sens0, rtol, atol, max_steps=2500):
+    def forward_sens(self, t0, tvals, y0, params, sens0, rtol, atol, max_steps=2500, pbar=None):
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)
         y0, params, B = self._prep(y0, params)
         n_t = len(tvals)
-        atol = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=np.float64), (self.ns,)))
+        # what sb_api.cpp uploads: atol per stacked component, sensitivity block k with atol / |pbar_k|
+        atol = np.broadcast_to(np.asarray(atol, dtype=np.float64), (self.ns,))
+        scale = np.ones(self.nd) if pbar is None else np.abs(np.asarray(pbar, dtype=np.float64))
+        atol = np.ascontiguousarray(np.concatenate([atol] + [atol / scale[k] for k in range(self.nd)]))
         sens0 = np.ascontiguousarray(sens0, dtype=np.float64)
         shared = int(sens0.ndim == 2)
         y_out = np.zeros((B, n_t, self.ns))

@@ -92,3 +92,124 @@ def test_hermite_table_entries(tmp_path):
             s0 = (evaluate(e, t0 + eps) - evaluate(e, t0 - eps)) / (2 * eps)
             np.testing.assert_allclose(s1, hist[idx, 2 + ns:], rtol=1e-6, atol=1e-9)
             np.testing.assert_allclose(s0, hist[idx - 1, 2 + ns:], rtol=1e-6, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------- constraints
+def chase_problem():
+    """Two states that test ``constraints``: ``a`` relaxes towards 0.6 + cos(t), which dips below
+    zero (a constraint on it cannot be met: CV_CONSTR_FAIL / CV_CONV_FAILURE after ten shrunken
+    steps), ``b`` decays towards zero, where at loose tolerances the unconstrained integrator
+    undershoots (a constraint on it is met by projection or by a smaller step)."""
+    import sympy as sy
+    from sunode_b200 import SympyProblem
+
+    def rhs(t, y, p):
+        return {'a': -p.k * (y.a - (0.6 + sy.cos(t))),
+                'b': -p.m * y.b * y.b - p.k * y.b * y.a}
+    return SympyProblem(params={'k': (), 'm': ()}, states={'a': (), 'b': ()}, rhs_sympy=rhs,
+                        derivative_params=[('k',), ('m',)])
+
+
+def chase_inputs(B=16):
+    rng = np.random.default_rng(0)
+    theta = np.array([20.0, 3.0]) * np.exp(0.3 * rng.standard_normal((B, 2)))
+    return np.array([1.6, 1.0]), theta, np.linspace(0.1, 6, 40)
+
+
+def constraint_define(cons):
+    return 'SB_CONSTRAINTS=' + ','.join('%.1f' % c for c in cons)
+
+
+def test_oracle_constraints_change_the_solution():
+    prob = chase_problem()
+    y0, theta, tv = chase_inputs()
+    free = Oracle(prob, rtol=1e-4, atol=1e-7).solve_forward(0.0, tv, y0, theta)
+    assert (free[1] == 0).all() and free[0][..., 1].min() < -1e-3      # undershoots without
+    con = Oracle(prob, rtol=1e-4, atol=1e-7, constraints=[0.0, 1.0]).solve_forward(0.0, tv, y0, theta)
+    assert (con[1] == 0).all()
+    assert con[0][..., 1].min() > -1e-6                  # dense output between non-negative steps
+    # a constraint the true solution violates cannot be met
+    bad = Oracle(prob, rtol=1e-4, atol=1e-7, constraints=[1.0, 0.0]).solve_forward(0.0, tv, y0, theta)
+    assert np.isin(bad[1], (-15, -4)).all() and (bad[1] == -15).any()
+    assert np.isnan(bad[0]).all()
+    # cvInitialSetup: y0 must satisfy the constraints
+    st0 = Oracle(prob, rtol=1e-4, atol=1e-7, constraints=[0.0, 2.0]).solve_forward(
+        0.0, tv, np.array([1.6, 0.0]), theta[:2])[1]
+    assert (st0 == -22).all()
+
+
+@pytest.mark.parametrize('cons', [[0.0, 1.0], [0.0, 2.0], [2.0, 1.0]])
+def test_device_constraints_match_oracle(cons, tmp_path):
+    """The SB_CONSTRAINTS build of the forward integrator (Bdf::check_constraints) against the
+    oracle's cvCheckConstraints: same outcomes per draw (including which draws give up with
+    CV_CONSTR_FAIL and which with CV_CONV_FAILURE), same step / failure counters except where a
+    rounding-level difference flips a sign test."""
+    prob = chase_problem()
+    y0, theta, tv = chase_inputs()
+    emu = Emulator(prob, str(tmp_path), defines=(constraint_define(cons),))
+    r = emu.forward(0.0, tv, y0, theta, 1e-4, 1e-7)
+    yo, so, sto = Oracle(prob, rtol=1e-4, atol=1e-7, constraints=cons).solve_forward(0.0, tv, y0, theta)
+    np.testing.assert_array_equal(r['status'], so)
+    assert (r['stats'][:, 0] == sto[:, 0]).mean() >= 0.8
+    assert (r['stats'][:, 5] == sto[:, 5]).mean() >= 0.8
+    ok = so == 0
+    if ok.any():
+        assert np.max(np.abs(r['y'][ok] - yo[ok]) / (1e-4 * np.abs(yo[ok]) + 1e-7)) <= 100.0
+    assert np.isnan(r['y'][~ok]).all()
+    bad0 = emu.forward(0.0, tv, np.array([1.6, -0.5]), theta[:2], 1e-4, 1e-7)
+    assert (bad0['status'] == -22).all()
+
+
+def test_constraints_leave_the_backward_pass_alone(tmp_path):
+    """AdjointSolver(constraints=...) constrains the forward ODE only (reference
+    solver.py:566-572 sets them on ``self._ode``): with flags that never bind the constrained
+    build reproduces the unconstrained adjoint bit for bit -- one lane per instance and lane
+    groups."""
+    for name, group in (('lv_adj', False), ('seir_adj', True)):
+        w, prob, y0, theta, grads = _case(name, 6)
+        cons = [1.0] * prob.n_states
+        ref = Emulator(prob, str(tmp_path), group=group).adjoint(
+            w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity, group=group)
+        con = Emulator(prob, str(tmp_path), defines=(constraint_define(cons),), group=group).adjoint(
+            w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity, group=group)
+        assert (con['status'] == 0).all()
+        np.testing.assert_array_equal(con['y'], ref['y'])
+        np.testing.assert_array_equal(con['grad'], ref['grad'])
+        np.testing.assert_array_equal(con['lamda'], ref['lamda'])
+
+
+# ---------------------------------------------------------------------------------- scaling factors
+def test_sens_scaling_factors(tmp_path):
+    """``Solver(scaling_factors=pbar)`` (reference solver.py:381-389: CVodeSetSensParams +
+    CVodeSensEEtolerances): sensitivity block k is controlled with atol / |pbar_k|.  Oracle:
+    pbar = 1 is the default run bit for bit, a large pbar tightens the sensitivity error control
+    (more steps); emulated device code = oracle."""
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(8)
+    s0 = np.zeros((2, 2))
+    base = Oracle(prob, rtol=1e-6, atol=1e-6).solve_forward_sens(w.t0, w.tvals, y0, theta, s0)
+    ones = Oracle(prob, rtol=1e-6, atol=1e-6, scaling_factors=np.ones(2)).solve_forward_sens(
+        w.t0, w.tvals, y0, theta, s0)
+    np.testing.assert_array_equal(base[1], ones[1])
+    pbar = np.array([1e4, -1e3])
+    scaled = Oracle(prob, rtol=1e-6, atol=1e-6, scaling_factors=pbar).solve_forward_sens(
+        w.t0, w.tvals, y0, theta, s0)
+    assert (scaled[2] == 0).all() and (scaled[3][:, 0] >= base[3][:, 0]).all()
+    assert not np.array_equal(scaled[1], base[1])
+    from tests.emu.emu import Emulator
+    r = Emulator(prob, str(tmp_path)).forward_sens(w.t0, w.tvals, y0, theta, s0, 1e-6, 1e-6, pbar=pbar)
+    assert (r['status'] == 0).all()
+    np.testing.assert_array_equal(r['stats'][:, 0], scaled[3][:, 0])
+    np.testing.assert_allclose(r['sens'], scaled[1], rtol=1e-7, atol=1e-9 * np.abs(scaled[1]).max())
+
+
+def test_constraint_flags_to_build_option():
+    from sunode_b200.solver import _constraint_defines
+    assert _constraint_defines(None, 3) == (None, ())
+    c, d = _constraint_defines(0.0, 2)
+    assert d == () and c.shape == (2,)                           # all-zero flags: the default build
+    c, d = _constraint_defines(np.array([1, 0, -2]), 3)
+    assert d == ('SB_CONSTRAINTS=1.0,0.0,-2.0',)
+    with pytest.raises(ValueError, match='CV_ILL_INPUT'):
+        _constraint_defines([3.0, 0.0], 2)

@@ -33,3 +33,74 @@ def test_hermite_interpolation_matches_oracle(name):
     plain = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=w.history_capacity)
     gp = plain.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)[1]
     assert np.max(np.abs(g - gp) / np.abs(gp).max(axis=0)) > 1e-12
+
+
+@pytest.mark.parametrize('cons', [[0.0, 1.0], [2.0, 1.0]])
+def test_constraints_match_oracle(cons):
+    """``Solver(constraints=...)`` (reference solver.py:268-271): the SB_CONSTRAINTS build of the
+    forward kernel against the oracle's cvCheckConstraints -- same outcome per draw, including the
+    draws that give up with CV_CONSTR_FAIL / CV_CONV_FAILURE (NaN rows)."""
+    from oracle.oracle import Oracle
+    from sunode_b200.solver import Solver
+    from tests.test_options import chase_inputs, chase_problem
+    prob = chase_problem()
+    y0, theta, tv = chase_inputs(64)
+    solver = Solver(prob, abstol=1e-7, reltol=1e-4, constraints=np.array(cons))
+    stats = np.zeros((len(theta), 8), dtype=np.int32)
+    y, status = solver.solve_batch(0.0, tv, np.tile(y0, (len(theta), 1)), theta, stats=stats)
+    yo, so, sto = Oracle(prob, rtol=1e-4, atol=1e-7, constraints=cons).solve_forward(0.0, tv, y0, theta)
+    # the sign tests of the constraint check are discontinuous: a rounding-level difference may
+    # flip one, after which the two step sequences differ (emulated device code vs oracle on these
+    # inputs: 98 % / 92 % of the draws end with the same flag, 74 % with the same step count)
+    assert ((status == 0) == (so == 0)).mean() >= 0.9
+    assert (status == so).mean() >= 0.75
+    assert np.isin(status, (0, -15, -4)).all()
+    both = (status == 0) & (so == 0)
+    if cons[0] == 0.0:
+        assert both.mean() >= 0.8
+        assert np.median(np.abs(y[both] - yo[both]) / (1e-4 * np.abs(yo[both]) + 1e-7)) <= 1.0
+        assert (stats[both, 0] == sto[both, 0]).mean() >= 0.5
+        assert y[status == 0][..., 1].min() > -1e-6
+    else:
+        assert (status != 0).all()              # a >= 0 cannot hold: the target dips below zero
+    assert np.isnan(y[status != 0]).all()
+
+
+def test_adjoint_with_inactive_constraints_is_unchanged():
+    """AdjointSolver(constraints=...) constrains the forward ODE only; flags that never bind
+    reproduce the unconstrained results bit for bit."""
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(128)
+    grads = np.ones((len(w.tvals), prob.n_states))
+    ref = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512).solve_adjoint_batch(
+        w.t0, w.tvals, y0, theta, grads)
+    con = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512,
+                        constraints=np.ones(2)).solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert (con[3] == 0).all()
+    for a, b in zip(ref[:3], con[:3]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_sens_scaling_factors_match_oracle():
+    """``Solver(sens_mode=..., scaling_factors=pbar)`` (reference solver.py:381-389) against the
+    oracle's CVodeSensEEtolerances weights (atol / |pbar_k| for sensitivity block k)."""
+    from oracle.oracle import Oracle
+    from sunode_b200.solver import Solver
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(64)
+    pbar = np.array([1e4, -1e3])
+    s0 = np.zeros((2, 2))
+    solver = Solver(prob, abstol=1e-6, reltol=1e-6, sens_mode='simultaneous', scaling_factors=pbar)
+    stats = np.zeros((64, 8), dtype=np.int32)
+    y, s, status = solver.solve_sens_batch(w.t0, w.tvals, y0, theta, s0, stats=stats)
+    yo, so, sto, statso = Oracle(prob, rtol=1e-6, atol=1e-6, scaling_factors=pbar).solve_forward_sens(
+        w.t0, w.tvals, y0, theta, s0)
+    assert (status == 0).all() and (sto == 0).all()
+    assert (stats[:, 0] == statso[:, 0]).mean() >= 0.9
+    assert np.max(np.abs(y - yo) / (1e-6 * np.abs(yo) + 1e-6)) <= 1.0
+    assert np.max(np.abs(s - so)) <= 1e-5 * np.abs(so).max()
+    plain = Solver(prob, abstol=1e-6, reltol=1e-6, sens_mode='simultaneous')
+    s1 = plain.solve_sens_batch(w.t0, w.tvals, y0, theta, s0)[1]
+    assert not np.array_equal(s1, s)
