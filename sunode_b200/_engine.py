@@ -35,8 +35,12 @@ def kernel_source_hash() -> str:
         for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh'):
             with open(os.path.join(_build.CSRC, name), 'rb') as fh:
                 h.update(fh.read())
-        # the compiler is part of the key: NVRTC versions generate different code
-        h.update(('nvrtc ' + _lib.nvrtc_version()).encode())
+        # the compiler is part of the key: NVRTC versions generate different code (where NVRTC
+        # cannot be loaded only cubins of an unknown compiler can be found -- none are shipped)
+        try:
+            h.update(('nvrtc ' + _lib.nvrtc_version()).encode())
+        except _lib.LibraryError:
+            h.update(b'nvrtc unavailable')
         _kernel_hash = h.hexdigest()[:16]
     return _kernel_hash
 
