@@ -388,6 +388,11 @@ class AdjointSolver(_ParamsMixin):
         # steps per checkpoint, solver.py:533,588); here the per-instance capacity is explicit
         self._history_capacity = int(history_capacity or min(int(checkpoint_n), 1024))
         self._engine.set_history_capacity(self._history_capacity)
+        # Without an explicit capacity the store grows like the reference's does (its checkpoints
+        # hold 500 000 steps): a host-memory solve whose instances ran out of history slots is
+        # repeated with four times the capacity, up to checkpoint_n steps / _HISTORY_BYTES_MAX.
+        self._history_auto = history_capacity is None
+        self._history_limit = int(checkpoint_n)
         self._set_tolerances(abstol, reltol)
         self._engine.set_tolerances_b(1e-10, 1e-10)        # solver.py:599
         self._engine.set_quad_tolerances_b(1e-10, 1e-10)   # solver.py:614
@@ -420,7 +425,27 @@ class AdjointSolver(_ParamsMixin):
 
     def set_history_capacity(self, n_steps: int) -> None:
         self._history_capacity = int(n_steps)
+        self._history_auto = False
         self._engine.set_history_capacity(self._history_capacity)
+
+    _HISTORY_BYTES_MAX = 32 << 30
+
+    def _grow_history(self, B: int, status, stats) -> bool:
+        """True when instances of a host-memory solve ran out of history slots (CV_TOO_MUCH_WORK
+        with every slot used) and the capacity could be raised; the caller then solves again."""
+        if not self._history_auto or _is_torch(status) or stats is None:
+            return False
+        full = (np.asarray(status) == CV_TOO_MUCH_WORK) & (np.asarray(stats)[:, 7] >= self._history_capacity)
+        if not full.any():
+            return False
+        n_s = self._problem.n_states
+        new = min(self._history_capacity * 4, max(self._history_limit, self._history_capacity))
+        per_step = 8 * ((2 * n_s + 2) + (10 + 6 * n_s))       # history point + table entry
+        if new <= self._history_capacity or B * new * per_step > self._HISTORY_BYTES_MAX:
+            return False
+        self._history_capacity = new
+        self._engine.set_history_capacity(new)
+        return True
 
     def make_output_buffers(self, tvals):
         y_vals = np.zeros((len(tvals), self._problem.n_states))
@@ -474,8 +499,13 @@ class AdjointSolver(_ParamsMixin):
         params = self._batch_params(params, B)
         y_out, status = _alloc_like(y0, y_out, (B, len(tvals), self._problem.n_states), status, B)
         self._engine.set_max_num_steps(self._mxstep, max_retries)
-        self._engine.forward(float(t0), tvals, y0, params, y_out, status, stats,
-                             store_history=True, stream=stream)
+        if stats is None and self._history_auto and not _is_torch(status):
+            stats = np.empty((B, 8), dtype=np.int32)
+        while True:
+            self._engine.forward(float(t0), tvals, y0, params, y_out, status, stats,
+                                 store_history=True, stream=stream)
+            if not self._grow_history(B, status, stats):
+                break
         self._last_forward = (B, len(tvals))
         return y_out, status
 
@@ -522,7 +552,12 @@ class AdjointSolver(_ParamsMixin):
         lamda_out = _alloc_out(y0, lamda_out, (B, n_s))
         self._engine.set_max_num_steps(self._mxstep, max_retries)
         self._engine.set_max_num_steps_b(self._mxstep_b, max_retries_backward)
-        self._engine.adjoint(float(t0), tvals, y0, params, grads, y_out, grad_out, lamda_out,
-                             status, stats_fwd, stats_bwd, stream=stream)
+        if stats_fwd is None and self._history_auto and not _is_torch(status):
+            stats_fwd = np.empty((B, 8), dtype=np.int32)
+        while True:
+            self._engine.adjoint(float(t0), tvals, y0, params, grads, y_out, grad_out, lamda_out,
+                                 status, stats_fwd, stats_bwd, stream=stream)
+            if not self._grow_history(B, status, stats_fwd):
+                break
         self._last_forward = (B, len(tvals))
         return y_out, grad_out, lamda_out, status

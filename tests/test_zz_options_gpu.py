@@ -104,3 +104,31 @@ def test_sens_scaling_factors_match_oracle():
     plain = Solver(prob, abstol=1e-6, reltol=1e-6, sens_mode='simultaneous')
     s1 = plain.solve_sens_batch(w.t0, w.tvals, y0, theta, s0)[1]
     assert not np.array_equal(s1, s)
+
+
+def test_history_store_grows_like_the_reference_checkpoints():
+    """The reference keeps up to 500 000 forward steps per checkpoint (solver.py:533,588); here
+    the per-instance history capacity is explicit.  Without an explicit capacity a host-memory
+    solve that ran out of slots is repeated with a larger store instead of failing: the stiff
+    Robertson problem needs ~1 100 steps, the default capacity is 1 024."""
+    w = examples.workloads()['robertson_adj']
+    prob = w.make_problem()
+    y0, theta = w.draws(32)
+    grads = np.ones((len(w.tvals), prob.n_states))
+    fixed = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=4096)
+    ref = fixed.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert (ref[3] == 0).all()
+    auto = AdjointSolver(prob, abstol=1e-8, reltol=1e-8)
+    assert auto._history_capacity == 1024
+    out = auto.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert auto._history_capacity == 4096 and (out[3] == 0).all()
+    for a, b in zip(ref[:3], out[:3]):
+        np.testing.assert_array_equal(a, b)
+    # same through the two-call form
+    auto2 = AdjointSolver(prob, abstol=1e-8, reltol=1e-8)
+    y, st = auto2.solve_forward_batch(w.t0, w.tvals, y0, theta)
+    assert (st == 0).all() and auto2._history_capacity == 4096
+    np.testing.assert_array_equal(y, ref[0])
+    # an explicit capacity is a hard limit
+    small = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=256)
+    assert (small.solve_forward_batch(w.t0, w.tvals, y0, theta)[1] == -1).all()
