@@ -42,7 +42,7 @@ def test_oracle_hermite_is_a_valid_adjoint():
 def test_device_hermite_matches_oracle(name, group, tmp_path):
     """The SB_HERMITE build of the device code (history with y', cubic table entries, unchanged
     backward integrator; one lane per instance and lane groups) takes the oracle's steps."""
-    w, prob, y0, theta, grads = _case(name, 12 if group else 32)
+    w, prob, y0, theta, grads = _case(name, 4 if group else 32)
     emu = Emulator(prob, str(tmp_path), defines=('SB_HERMITE',), group=group)
     r = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity,
                     group=group)
@@ -52,7 +52,8 @@ def test_device_hermite_matches_oracle(name, group, tmp_path):
     assert np.max(np.abs(r['y'] - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-3
     assert np.max(np.abs(r['grad'] - go) / np.abs(go).max(axis=0)) <= 1e-9
     assert np.max(np.abs(r['lamda'] - lo) / np.abs(lo).max(axis=0)) <= 1e-9
-    assert (r['stats'][:, 0] == sto[:, 7]).mean() >= 0.9
+    # same step sequence up to the odd rounding-level flip of a controller decision
+    assert np.max(np.abs(r['stats'][:, 0] - sto[:, 7]) / sto[:, 7]) <= 0.02
     # and the polynomial oracle gives a (slightly) different answer: the option is not a no-op
     gp = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(w.t0, w.tvals, y0, theta, grads)[1]
     assert np.max(np.abs(r['grad'] - gp) / np.abs(gp).max(axis=0)) > 1e-12
@@ -164,9 +165,9 @@ def test_constraints_leave_the_backward_pass_alone(tmp_path):
     """AdjointSolver(constraints=...) constrains the forward ODE only (reference
     solver.py:566-572 sets them on ``self._ode``): with flags that never bind the constrained
     build reproduces the unconstrained adjoint bit for bit -- one lane per instance and lane
-    groups."""
+    groups (3 draws: the group emulation runs its lanes as threads)."""
     for name, group in (('lv_adj', False), ('seir_adj', True)):
-        w, prob, y0, theta, grads = _case(name, 6)
+        w, prob, y0, theta, grads = _case(name, 3)
         cons = [1.0] * prob.n_states
         ref = Emulator(prob, str(tmp_path), group=group).adjoint(
             w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity, group=group)
