@@ -31,6 +31,7 @@ L2_FLUSH_BYTES = 512 << 20
 
 
 BACKWARD_TOL = 1e-10        # --backward-tol
+INTERPOLATION = 'polynomial'   # --interpolation
 
 
 def parse_args():
@@ -47,6 +48,8 @@ def parse_args():
     ap.add_argument('--cpu-sample', type=int, default=None, help='instances in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--interpolation', default='polynomial', choices=['polynomial', 'hermite'],
+                    help='AdjointSolver(interpolation=...) (reference default: polynomial)')
     ap.add_argument('--backward-tol', type=float, default=1e-10,
                     help='rtol = atol of the backward problem and its quadrature (the reference '
                          'hard-codes 1e-10, solver.py:599,614; README.md:243-249 shows the override)')
@@ -133,7 +136,7 @@ def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
     """The oracle (CPU restatement of the reference path) on the host cores, bounded sample."""
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8, rtol_b=BACKWARD_TOL, atol_b=BACKWARD_TOL,
-                 rtol_q=BACKWARD_TOL, atol_q=BACKWARD_TOL)
+                 rtol_q=BACKWARD_TOL, atol_q=BACKWARD_TOL, interpolation=INTERPOLATION)
     y0, theta = w.draws(n_sample)
     grads = w.grads(problem.n_states)
     cores = threads or host_threads()
@@ -155,7 +158,7 @@ def run_reference(args, w, problem, rank, world):
     n_sample = args.cpu_sample or {'lv_adj': 16384, 'lv_fwd': 65536}.get(w.name, 1024)
     from oracle.oracle import Oracle, max_threads
     orc = Oracle(problem, rtol=1e-8, atol=1e-8, rtol_b=BACKWARD_TOL, atol_b=BACKWARD_TOL,
-                 rtol_q=BACKWARD_TOL, atol_q=BACKWARD_TOL)
+                 rtol_q=BACKWARD_TOL, atol_q=BACKWARD_TOL, interpolation=INTERPOLATION)
     y0, theta = w.draws(n_sample)
     grads = w.grads(problem.n_states)
     cores = host_threads()
@@ -200,6 +203,7 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
         'batch_per_gpu': int(batch), 'global_batch': int(batch) * n_gpus,
         'rtol': 1e-8, 'atol': 1e-8, 'rtol_backward': BACKWARD_TOL, 'atol_backward': BACKWARD_TOL,
         'method': 'BDF(1-5) + Newton/dense LU; adjoint: backward BDF restarted at every tval + quadrature',
+        'interpolation': INTERPOLATION,
         'cotangent': ('ones((n_t, n_s))' if w.cotangent == 'ones' else 'seeded N(0,1) [n_t, n_s]')
                      + ' shared by all instances',
         'theta': 'theta_med * exp(%g * N(0,1)), seed %d' % (w.sigma, w.seed),
@@ -211,9 +215,10 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
 
 
 def main():
-    global BACKWARD_TOL
+    global BACKWARD_TOL, INTERPOLATION
     args = parse_args()
     BACKWARD_TOL = float(args.backward_tol)
+    INTERPOLATION = args.interpolation
     from sunode_b200 import examples
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -242,7 +247,7 @@ def main():
     y0_h, theta_h = w.draws(B, offset=rank * B)
     grads_h = w.grads(n_s)
     if w.adjoint:
-        solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8,
+        solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8, interpolation=INTERPOLATION,
                                history_capacity=w.history_capacity, device=local_rank,
                                block_threads=args.block, min_blocks=args.min_blocks)
         if BACKWARD_TOL != 1e-10:
