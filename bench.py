@@ -224,7 +224,10 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     w = examples.workloads()[args.workload]
+    t_setup = time.perf_counter()
     problem = w.make_problem()
+    _ = problem.generated              # sympy derivation + code generation (outside every timed region)
+    codegen_s = time.perf_counter() - t_setup
 
     if args.impl == 'reference':
         run_reference(args, w, problem, rank, world)
@@ -246,6 +249,7 @@ def main():
     n_t, n_s, n_all, n_d = len(w.tvals), problem.n_states, problem.n_params_total, problem.n_params
     y0_h, theta_h = w.draws(B, offset=rank * B)
     grads_h = w.grads(n_s)
+    t_setup = time.perf_counter()
     if w.adjoint:
         solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8, interpolation=INTERPOLATION,
                                history_capacity=w.history_capacity, device=local_rank,
@@ -257,6 +261,10 @@ def main():
         solver = Solver(problem, abstol=1e-8, reltol=1e-8, device=local_rank,
                         block_threads=args.block, min_blocks=args.min_blocks)
     eng = solver._engine
+    # JIT / codegen are excluded from the metric and reported separately
+    setup = {'codegen_s': round(codegen_s, 3),
+             'kernel_build_s': round(time.perf_counter() - t_setup, 3),
+             'note': 'sympy -> CUDA source; NVRTC compile or in-tree cubin cache load + handle creation'}
 
     # ---- device-resident inputs / outputs (the `value` leg)
     y0_d = torch.from_numpy(y0_h).to(dev)
@@ -430,6 +438,7 @@ def main():
             'failed_instances': n_fail, 'failed_status_rank0': fail_codes,
             'collective': 'all_gather(y_out) + all_gather(grad|lamda0) per step' if gather else 'none'}),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+        'setup': setup,
     }
     if not args.no_cpu_baseline:
         # ~20-40 s of CPU work for the LV workload (spread over the host threads)
