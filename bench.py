@@ -32,6 +32,7 @@ L2_FLUSH_BYTES = 512 << 20
 
 BACKWARD_TOL = 1e-10        # --backward-tol
 INTERPOLATION = 'polynomial'   # --interpolation
+BACKWARD = 'reference'         # --backward
 
 
 def parse_args():
@@ -50,6 +51,10 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--interpolation', default='polynomial', choices=['polynomial', 'hermite'],
                     help='AdjointSolver(interpolation=...) (reference default: polynomial)')
+    ap.add_argument('--backward', default='reference', choices=['reference', 'fundamental'],
+                    help='backward schedule: the reference\'s restart per output time (default, the '
+                         'parity path) or the restart-free fundamental-matrix pass (opt-in, '
+                         'csrc/sb_fund.cuh; the CPU arms always run the reference schedule)')
     ap.add_argument('--backward-tol', type=float, default=1e-10,
                     help='rtol = atol of the backward problem and its quadrature (the reference '
                          'hard-codes 1e-10, solver.py:599,614; README.md:243-249 shows the override)')
@@ -203,7 +208,7 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
         'batch_per_gpu': int(batch), 'global_batch': int(batch) * n_gpus,
         'rtol': 1e-8, 'atol': 1e-8, 'rtol_backward': BACKWARD_TOL, 'atol_backward': BACKWARD_TOL,
         'method': 'BDF(1-5) + Newton/dense LU; adjoint: backward BDF restarted at every tval + quadrature',
-        'interpolation': INTERPOLATION,
+        'interpolation': INTERPOLATION, 'backward_schedule': BACKWARD,
         'cotangent': ('ones((n_t, n_s))' if w.cotangent == 'ones' else 'seeded N(0,1) [n_t, n_s]')
                      + ' shared by all instances',
         'theta': 'theta_med * exp(%g * N(0,1)), seed %d' % (w.sigma, w.seed),
@@ -215,10 +220,11 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
 
 
 def main():
-    global BACKWARD_TOL, INTERPOLATION
+    global BACKWARD_TOL, INTERPOLATION, BACKWARD
     args = parse_args()
     BACKWARD_TOL = float(args.backward_tol)
     INTERPOLATION = args.interpolation
+    BACKWARD = args.backward if args.impl != 'reference' else 'reference'   # CPU arms: reference schedule
     from sunode_b200 import examples
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -252,7 +258,7 @@ def main():
     t_setup = time.perf_counter()
     if w.adjoint:
         solver = AdjointSolver(problem, abstol=1e-8, reltol=1e-8, interpolation=INTERPOLATION,
-                               history_capacity=w.history_capacity, device=local_rank,
+                               backward=BACKWARD, history_capacity=w.history_capacity, device=local_rank,
                                block_threads=args.block, min_blocks=args.min_blocks)
         if BACKWARD_TOL != 1e-10:
             solver.set_backward_tolerances(BACKWARD_TOL, BACKWARD_TOL)
@@ -402,14 +408,18 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get('%s:%d:%s' % (w.name, B, 'sb_backward' if w.adjoint else 'sb_forward'))
+        if BACKWARD == 'fundamental':
+            traffic = None          # no ncu capture of sb_backward_fund yet
     from sunode_b200._engine import lanes_per_instance, FLAT_FWD_STEPS_PER_TVAL
     group = lanes_per_instance(n_s)
     # which build of the backward kernel did the work (the device-side rule of sb_api.cpp)
     flat = w.adjoint and group == 1 and mean_fwd_steps * (1 - n_fail / max(B, 1)) > FLAT_FWD_STEPS_PER_TVAL * n_t
     roofline = {
-        'bound': 'hbm', 'kernel': ('sb_backward_flat' if flat else 'sb_backward') if w.adjoint else 'sb_forward',
+        'bound': 'hbm', 'kernel': ('sb_backward_fund' if BACKWARD == 'fundamental' else
+                                   'sb_backward_flat' if flat else 'sb_backward') if w.adjoint else 'sb_forward',
         'lanes_per_instance': {'forward': 1, 'backward': group if w.adjoint else None},
         'backward_schedule': None if not w.adjoint else (
+            'restart-free (fundamental matrix), one lane per instance' if BACKWARD == 'fundamental' else
             'every lane walks its intervals on its own' if flat else 'lanes of a warp restart together'),
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
         'traffic': traffic, 'traffic_source': 'ncu --set full capture, profiles/ncu_traffic.json' if traffic else None,

@@ -32,7 +32,7 @@ def kernel_source_hash() -> str:
     global _kernel_hash
     if _kernel_hash is None:
         h = hashlib.sha256()
-        for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh'):
+        for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh', 'sb_fund.cuh'):
             with open(os.path.join(_build.CSRC, name), 'rb') as fh:
                 h.update(fh.read())
         # the compiler is part of the key: NVRTC versions generate different code (where NVRTC

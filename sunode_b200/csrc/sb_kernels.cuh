@@ -683,6 +683,9 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
 
 }  // namespace sb
 
+#ifdef SB_FUND
+#include "sb_fund.cuh"
+#endif
 #ifdef SB_HOST_EMULATION_GROUP
 #include "sb_group.cuh"
 #endif
@@ -708,6 +711,15 @@ sb_forward_sens(const __grid_constant__ SbForwardArgs a) {
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long inst = warp * a.lanes + lane;
     sb::forward_sens_instance(a, inst, lane < a.lanes && inst < a.B);
+}
+#endif
+
+#ifdef SB_FUND
+// restart-free backward pass (sb_fund.cuh): one lane per instance, grid = ceil(B / 32) warps
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+sb_backward_fund(const __grid_constant__ SbBackwardArgs a) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    sb::backward_fund_instance(a, inst, inst < a.B);
 }
 #endif
 

@@ -364,6 +364,7 @@ class AdjointSolver(_ParamsMixin):
 
     def __init__(self, problem: Problem, *, abstol=1e-10, reltol=1e-10, checkpoint_n=500_000,
                  interpolation='polynomial', constraints=None, solver='BDF', adjoint_solver='BDF',
+                 backward: str = 'reference',
                  device: Optional[int] = None, history_capacity: Optional[int] = None,
                  block_threads: Optional[int] = None, min_blocks: Optional[int] = None):
         if solver not in ('BDF', 'ADAMS'):
@@ -382,6 +383,20 @@ class AdjointSolver(_ParamsMixin):
         # CV_HERMITE (solver.py:581-586): the forward kernel also stores y' at every step and the
         # table kernel writes cubic Hermite entries; a build option of the kernels (csrc/sb_args.h)
         defines = (('SB_HERMITE',) if interpolation == 'hermite' else ()) + constraint_defines
+        # backward='fundamental' (not a reference option): the restart-free
+        # backward pass of csrc/sb_fund.cuh -- the fundamental matrix of the adjoint equation is
+        # integrated without restarts and the jumps at the output times become small dense
+        # solves.  Same results to the tolerances, ~6x fewer backward steps on smooth problems;
+        # the default keeps the reference's restart-per-output-time schedule.
+        if backward not in ('reference', 'fundamental'):
+            raise ValueError(f'Unknown backward schedule {backward}.')
+        if backward == 'fundamental':
+            if problem.n_states > 4:
+                raise NotImplementedError(
+                    'backward="fundamental" integrates n_states^2 + n_states * n_params components '
+                    'per lane; it is implemented for up to 4 states.')
+            defines = defines + ('SB_FUND',)
+        self._backward = backward
         self._engine = Engine(problem.generated, device=device, block_threads=block_threads,
                               min_blocks=min_blocks, defines=defines)
         # the reference keeps every forward step of one solve in memory (checkpoint_n = 500 000
@@ -519,6 +534,8 @@ class AdjointSolver(_ParamsMixin):
         ``(grad_out[B, n_deriv], lamda_out[B, n_states], status[B])``."""
         if self._last_forward is None:
             raise SolverError('solve_backward called before solve_forward.')
+        if self._backward == 'fundamental' and (lamda_all_out is not None or quad_all_out is not None):
+            raise NotImplementedError('lamda_all_out / quad_all_out need backward="reference".')
         B, n_t = self._last_forward
         tvals = np.asarray(tvals, dtype=np.float64)
         if params is not None:

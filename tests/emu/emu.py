@@ -128,7 +128,7 @@ class Emulator:
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,
                 rtol_q=1e-10, atol_q=1e-10, hist_cap=1024, max_steps_b=25000, flat=None,
-                group=False):
+                group=False, fund=False):
         B0 = max(len(np.atleast_2d(y0)), len(np.atleast_2d(params)))
         tab_fused = np.zeros((B0, hist_cap, 10 + 6 * self.ns))
         fwd = self.forward(t0, tvals, y0, params, rtol, atol, hist_cap=hist_cap,
@@ -155,7 +155,9 @@ class Emulator:
                           _ip(fwd['hist_n']), _ip(fwd['status']), gptr, _dp(lam_out),
                           _ip(status), _ip(stats), B, n_t, hist_cap, max_steps_b, shared, None, None,
                           None, None, None, None, 1, n_t + 1, 0, 32, -1 if flat is None else flat, 0, None, 0)
-        if group:
+        if fund:
+            self.lib.emu_backward_fund(ctypes.byref(ba))
+        elif group:
             assert self.lib.emu_group_size() > 1, 'this problem does not run in lane groups'
             self.lib.emu_backward_group(ctypes.byref(ba))
         else:

@@ -37,6 +37,12 @@ void emu_backward_flat(const SbBackwardArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
     for (long long i = 0; i < a->B; ++i) sb::backward_instance_flat(*a, i, true);
 }
+#ifdef SB_FUND
+void emu_backward_fund(const SbBackwardArgs* a) {
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < a->B; ++i) sb::backward_fund_instance(*a, i, true);
+}
+#endif
 void emu_backward_unit(const SbBackwardArgs* a, int k0, int k1) {
     #pragma omp parallel for schedule(dynamic, 16)
     for (long long i = 0; i < a->B; ++i) sb::backward_unit<false>(*a, i, true, k0, k1);

@@ -214,3 +214,50 @@ def test_constraint_flags_to_build_option():
     assert d == ('SB_CONSTRAINTS=1.0,0.0,-2.0',)
     with pytest.raises(ValueError, match='CV_ILL_INPUT'):
         _constraint_defines([3.0, 0.0], 2)
+
+
+# ---------------------------------------------------------------------------------- restart-free backward
+@pytest.mark.parametrize('name', ['lv_adj', 'robertson_adj'])
+def test_fundamental_matrix_backward_pass(name, tmp_path):
+    """SURVEY.md 8(f) #3, ``AdjointSolver(backward='fundamental')`` (csrc/sb_fund.cuh): the
+    fundamental matrix of the adjoint equation integrated without restarts, jumps as dense solves.
+    Same gradients as the reference's restart-per-output-time schedule to the tolerances (both
+    are equally far from a 1e-12 solve); on the smooth problem a sixth of the backward steps and
+    no re-basing, on the stiff one the conditioning guard re-bases at most output times."""
+    w, prob, y0, theta, grads = _case(name, 16)
+    emu = Emulator(prob, str(tmp_path), defines=('SB_FUND',))
+    r = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=w.history_capacity, fund=True)
+    ref = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(w.t0, w.tvals, y0, theta, grads)
+    tight = Oracle(prob, rtol=1e-12, atol=1e-12, rtol_b=1e-12, atol_b=1e-12, rtol_q=1e-12,
+                   atol_q=1e-12, mxstep=20000, mxstep_b=20000).solve_adjoint(w.t0, w.tvals, y0, theta, grads)
+    assert (r['status'] == 0).all() and (ref[3] == 0).all() and (tight[3] == 0).all()
+    gs, ls = np.abs(tight[1]).max(axis=0), np.abs(tight[2]).max(axis=0)
+    err_fund = np.max(np.abs(r['grad'] - tight[1]) / gs)
+    err_ref = np.max(np.abs(ref[1] - tight[1]) / gs)
+    assert err_fund <= 1e-5 and err_fund <= 3 * err_ref + 1e-8       # SURVEY 8(c) envelope at 1e-8
+    # (lamda(t0) of the stiff problem is the less accurate output of either schedule)
+    assert np.max(np.abs(r['lamda'] - tight[2]) / ls) <= max(1e-5, 3 * np.max(np.abs(ref[2] - tight[2]) / ls))
+    steps, rebases, steps_ref = r['stats'][:, 0], r['stats'][:, 7], ref[4][:, 7]
+    if name == 'lv_adj':
+        assert np.max(np.abs(r['grad'] - ref[1]) / gs) <= 1e-7
+        assert (rebases == 0).all() and (steps < 0.3 * steps_ref).all()
+    else:
+        assert (rebases > 10).all() and (steps < 1.5 * steps_ref).all()
+
+
+def test_fundamental_matrix_backward_edge_cases(tmp_path):
+    """Output times that include t0, a last output time before t_start's interval is empty, a
+    single output time, all-t0 outputs: the restart-free pass against the reference schedule."""
+    w, prob, y0, theta, _ = _case('lv_adj', 4)
+    emu = Emulator(prob, str(tmp_path), defines=('SB_FUND',))
+    rng = np.random.default_rng(9)
+    for tv in (np.linspace(0, 10, 7), np.linspace(0.5, 9, 5), np.array([3.0]), np.array([0.0]),
+               np.array([0.0, 0.0, 2.0, 2.0, 5.0])):
+        g = rng.standard_normal((4, len(tv), 2))
+        r = emu.adjoint(w.t0, tv, y0, theta, g, 1e-8, 1e-8, hist_cap=512, fund=True)
+        ref = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(w.t0, tv, y0, theta, g)
+        assert (r['status'] == 0).all() and (ref[3] == 0).all(), tv
+        scale = np.abs(ref[1]).max() + 1e-300
+        np.testing.assert_allclose(r['grad'], ref[1], rtol=0, atol=2e-7 * scale + 1e-14, err_msg=str(tv))
+        np.testing.assert_allclose(r['lamda'], ref[2], rtol=0, atol=2e-7 * np.abs(ref[2]).max() + 1e-14,
+                                   err_msg=str(tv))

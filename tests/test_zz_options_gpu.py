@@ -144,3 +144,34 @@ def test_history_store_grows_like_the_reference_checkpoints():
     # an explicit capacity is a hard limit
     small = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=256)
     assert (small.solve_forward_batch(w.t0, w.tvals, y0, theta)[1] == -1).all()
+
+
+def test_fundamental_matrix_backward_pass():
+    """``AdjointSolver(backward='fundamental')`` (csrc/sb_fund.cuh): the
+    restart-free backward kernel against the oracle's reference schedule -- same gradients to
+    1e-7 relative, a fraction of the backward steps, fused and two-call forms."""
+    from oracle.oracle import Oracle
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    B = 512
+    y0, theta = w.draws(B)
+    grads = np.random.default_rng(5).standard_normal((B, len(w.tvals), prob.n_states))
+    solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512, backward='fundamental')
+    stats = np.zeros((B, 8), dtype=np.int32)
+    y, g, lam, status = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_bwd=stats)
+    yo, go, lo, so, sto = Oracle(prob, rtol=1e-8, atol=1e-8).solve_adjoint(w.t0, w.tvals, y0, theta, grads)
+    assert (status == 0).all() and (so == 0).all()
+    assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1.0
+    assert np.max(np.abs(g - go) / np.abs(go).max(axis=0)) <= 1e-7
+    assert np.max(np.abs(lam - lo) / np.abs(lo).max(axis=0)) <= 1e-7
+    assert (stats[:, 0] < 0.3 * sto[:, 7]).all() and (stats[:, 7] == 0).all()
+    y2, st2 = solver.solve_forward_batch(w.t0, w.tvals, y0, theta)
+    g2, l2, sb2 = solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
+    assert (sb2 == 0).all()
+    np.testing.assert_array_equal(g2, g)
+    np.testing.assert_array_equal(l2, lam)
+    with pytest.raises(NotImplementedError):
+        solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads,
+                                    lamda_all_out=np.empty((B, len(w.tvals), 2)))
+    with pytest.raises(NotImplementedError):
+        AdjointSolver(examples.seir(), backward='fundamental')

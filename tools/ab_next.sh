@@ -5,7 +5,10 @@
 #  2. the headline workload compiled by the toolkit's NVRTC 12.9 (default) against torch's
 #     NVRTC 12.8 (the LV cubin used to come from whichever the process had loaded);
 #  3. the reference README's backward-tolerance override (1e-8 instead of the hard-coded 1e-10,
-#     SURVEY.md 8(d) asks for both) and Hermite interpolation, device-resident legs only.
+#     SURVEY.md 8(d) asks for both), the restart-free fundamental-matrix backward pass
+#     (--backward fundamental: ~6x fewer backward steps on LV, one lane per instance, spills
+#     328 B -- the number that decides whether the lane-per-column layout is worth building)
+#     and Hermite interpolation, device-resident legs only.
 set -x
 O=gpurun_out
 mkdir -p $O
@@ -17,6 +20,7 @@ SUNODE_B200_NVRTC=$NVRTC128 python bench.py $Q > $O/ab_lv_nvrtc128.json 2> $O/ab
 SUNODE_B200_NVRTC=$NVRTC128 python bench.py --workload seir_adj --batch 32768 $Q > $O/ab_seir_nvrtc128.json 2> $O/ab_seir_nvrtc128.err
 python bench.py --workload seir_adj --batch 32768 $Q > $O/ab_seir_nvrtc129.json 2> $O/ab_seir_nvrtc129.err
 python bench.py --backward-tol 1e-8 $Q > $O/ab_lv_bwdtol1e-8.json 2> $O/ab_lv_bwdtol.err
+python bench.py --backward fundamental $Q > $O/ab_lv_fundamental.json 2> $O/ab_lv_fundamental.err
 python bench.py --interpolation hermite $Q > $O/ab_lv_hermite.json 2> $O/ab_lv_hermite.err
 for f in $O/ab_*.json; do python - "$f" <<'PY'
 import json, sys
