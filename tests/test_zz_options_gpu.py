@@ -164,7 +164,7 @@ def test_fundamental_matrix_backward_pass():
     assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1.0
     assert np.max(np.abs(g - go) / np.abs(go).max(axis=0)) <= 1e-7
     assert np.max(np.abs(lam - lo) / np.abs(lo).max(axis=0)) <= 1e-7
-    assert (stats[:, 0] < 0.3 * sto[:, 7]).all() and (stats[:, 7] == 0).all()
+    assert (stats[:, 0] < 0.35 * sto[:, 7]).all() and (stats[:, 7] == 0).all()   # emulated: <= 0.24, mean 0.145
     y2, st2 = solver.solve_forward_batch(w.t0, w.tvals, y0, theta)
     g2, l2, sb2 = solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
     assert (sb2 == 0).all()
