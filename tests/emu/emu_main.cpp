@@ -67,6 +67,7 @@ void emu_backward_group(const SbBackwardArgs* a) {
     pthread_barrier_destroy(&emu_group.bar);
 }
 #endif
+int emu_hist_stride() { return sb::HIST_STRIDE; }   // what the cubin exports as sb_hist_stride
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
 // sizeof the argument blocks as the C++ side sees them (checked against the ctypes mirrors)
 void emu_arg_sizes(int* fwd, int* tab, int* bwd, int* ev) {

@@ -1,0 +1,125 @@
+"""Child process of tests/test_host_logic.py: runs the product's Python layer and C-ABI library on
+top of tests/emu/fake_cuda.cpp (LD_LIBRARY_PATH is set by the parent) and compares what comes out
+with the same emulated kernels called directly.  TEST INFRASTRUCTURE ONLY."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from sunode_b200 import _lib, examples                       # noqa: E402
+from sunode_b200.solver import AdjointSolver, Solver         # noqa: E402
+from tests.emu.emu import Emulator                           # noqa: E402
+from tests.test_options import chase_inputs, chase_problem, constraint_define   # noqa: E402
+
+work = tempfile.mkdtemp()
+assert _lib.device_count() == 1
+
+# the fake driver never looks inside a cubin (the kernels it runs are the emulation library's), so
+# NVRTC -- which would talk to the real driver -- is kept out of this process
+from sunode_b200 import _engine                               # noqa: E402
+_engine.compile_cubin = lambda gen, **kw: (b'\x7fELF' + bytes(60), '<not compiled>')
+
+
+def emulator(problem, defines=()):
+    emu = Emulator(problem, work, defines=defines)
+    os.environ['SB_FAKE_EMU_LIB'] = emu.lib._name      # read by the fake driver at module load
+    return emu
+
+
+w = examples.workloads()['lv_adj']
+prob = w.make_problem()
+B = 40                                                   # not a multiple of 32: padding lanes
+y0, theta = w.draws(B)
+grads = np.random.default_rng(1).standard_normal((B, len(w.tvals), 2))
+
+# 1. the default path: fused call, two-call form, shared cotangent, stats routing
+emu = emulator(prob)
+ref = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512)
+solver = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+sf, sb = np.zeros((B, 8), np.int32), np.zeros((B, 8), np.int32)
+y, g, lam, st = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_fwd=sf, stats_bwd=sb)
+assert (st == 0).all()
+for a, b in ((y, ref['y']), (g, ref['grad']), (lam, ref['lamda']), (sf, ref['fwd']['stats']), (sb[:, :7], ref['stats'][:, :7])):
+    np.testing.assert_array_equal(a, b)
+y2, st2 = solver.solve_forward_batch(w.t0, w.tvals, y0, theta)
+g2, l2, sb2 = solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
+np.testing.assert_array_equal(g2, g)
+np.testing.assert_array_equal(l2, lam)
+print('default path ok')
+
+# 2. Hermite: the history stride comes back from the module, tables are cubic entries
+emu = emulator(prob, ('SB_HERMITE',))
+ref = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512)
+out = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512,
+                    interpolation='hermite').solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+assert (out[3] == 0).all()
+np.testing.assert_array_equal(out[1], ref['grad'])
+np.testing.assert_array_equal(out[2], ref['lamda'])
+assert not np.array_equal(out[1], g)
+print('hermite ok')
+
+# 3. restart-free backward pass: kernel selection in the launcher
+emu = emulator(prob, ('SB_FUND',))
+ref = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512, fund=True)
+fs = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512, backward='fundamental')
+sb = np.zeros((B, 8), np.int32)
+out = fs.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_bwd=sb)
+assert (out[3] == 0).all()
+np.testing.assert_array_equal(out[1], ref['grad'])
+np.testing.assert_array_equal(out[2], ref['lamda'])
+np.testing.assert_array_equal(sb, ref['stats'])
+assert sb[:, 0].mean() < 0.25 * ref['fwd']['stats'][:, 0].mean() * 20      # ~250 against ~1 660
+np.testing.assert_allclose(out[1], g, rtol=0, atol=1e-7 * np.abs(g).max())
+try:
+    fs.solve_forward_batch(w.t0, w.tvals, y0, theta)
+    fs.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=np.empty((B, 50, 2)))
+    raise SystemExit('traces must be refused')
+except NotImplementedError:
+    pass
+print('fundamental ok')
+
+# 4. history growth: default capacity forced down, the solve is repeated with a larger store
+emulator(prob)
+auto = AdjointSolver(prob, abstol=1e-8, reltol=1e-8)
+auto._history_capacity = 32
+auto._engine.set_history_capacity(32)
+out = auto.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+assert auto._history_capacity in (128, 512) and (out[3] == 0).all(), auto._history_capacity   # 32 -> 128 (-> 512)
+np.testing.assert_array_equal(out[1], g)
+fixed = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=32)
+st = fixed.solve_forward_batch(w.t0, w.tvals, y0, theta)[1]
+assert (st == -1).all()
+print('history growth ok')
+
+# 5. forward sensitivities with scaling factors: per-component tolerance array
+pbar = np.array([1e4, -1e3])
+emu = emulator(prob)
+s0 = np.zeros((2, 2))
+ref = emu.forward_sens(w.t0, w.tvals, y0, theta, s0, 1e-6, 1e-6, pbar=pbar)
+ys, ss, st = Solver(prob, abstol=1e-6, reltol=1e-6, sens_mode='simultaneous',
+                    scaling_factors=pbar).solve_sens_batch(w.t0, w.tvals, y0, theta, s0)
+assert (st == 0).all()
+np.testing.assert_array_equal(ss, ref['sens'])
+ref1 = emu.forward_sens(w.t0, w.tvals, y0, theta, s0, 1e-6, 1e-6)
+ss1 = Solver(prob, abstol=1e-6, reltol=1e-6, sens_mode='simultaneous').solve_sens_batch(
+    w.t0, w.tvals, y0, theta, s0)[1]
+np.testing.assert_array_equal(ss1, ref1['sens'])
+assert not np.array_equal(ss1, ss)
+print('sens scaling ok')
+
+# 6. constraints: status codes and NaN rows reach the caller
+cprob = chase_problem()
+cy0, ctheta, ctv = chase_inputs(16)
+for cons in ([0.0, 1.0], [2.0, 1.0]):
+    emu = emulator(cprob, (constraint_define(cons),))
+    ref = emu.forward(0.0, ctv, cy0, ctheta, 1e-4, 1e-7)
+    yc, stc = Solver(cprob, abstol=1e-7, reltol=1e-4, constraints=np.array(cons)).solve_batch(
+        0.0, ctv, np.tile(cy0, (16, 1)), ctheta)
+    np.testing.assert_array_equal(stc, ref['status'])
+    np.testing.assert_array_equal(yc, ref['y'])
+print('constraints ok')
+print('ALL OK')
