@@ -49,6 +49,21 @@ y2, st2 = solver.solve_forward_batch(w.t0, w.tvals, y0, theta)
 g2, l2, sb2 = solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
 np.testing.assert_array_equal(g2, g)
 np.testing.assert_array_equal(l2, lam)
+# the same call with mem = SB_MEM_DEVICE (what torch CUDA tensors select; here "device" memory is
+# host memory): no staging, status copied device-to-device, asynchronous until sb_synchronize
+import ctypes                                                # noqa: E402
+eng = solver._engine
+yd, gd, ld = np.full_like(y, -1.0), np.full_like(g, -1.0), np.full_like(lam, -1.0)
+std = np.full(B, 77, np.int32)
+ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)            # noqa: E731
+tv = np.ascontiguousarray(w.tvals)
+_lib.check(eng._lib.sb_solve_adjoint(eng._h, B, float(w.t0), tv.ctypes.data, len(tv), ptr(y0), ptr(theta),
+                                     ptr(grads), 0, ptr(yd), ptr(gd), ptr(ld), ptr(std), None, None,
+                                     _lib.SB_MEM_DEVICE, None))
+eng.synchronize()
+for a, b in ((yd, y), (gd, g), (ld, lam), (std, st)):
+    np.testing.assert_array_equal(a, b)
+assert eng.launch_count() > 0 and all(ms >= 0 for ms in eng.last_kernel_ms())
 print('default path ok')
 
 # 2. Hermite: the history stride comes back from the module, tables are cubic entries
