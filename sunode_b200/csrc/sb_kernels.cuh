@@ -681,6 +681,39 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
     backward_unit<true>(a, inst, valid, 0, a.n_t + 1);
 }
 
+// ------------------------------------------------------------------------------------ eval
+// One evaluation of a generated function (sb_eval): kind 0 rhs, 1 jacobian, 2 adjoint rhs,
+// 3 quadrature rhs.
+__device__ __forceinline__ void eval_instance(const SbEvalArgs& a, long long i) {
+    double y[NS], p[NP_], lam[NS];
+    const double t = a.t[i];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) { y[k] = a.y[i * NS + k]; lam[k] = a.lam ? a.lam[i * NS + k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = a.params_shared ? a.params[k] : a.params[i * NP + k];
+    if (a.kind == 0) {
+        double out[NS];
+        sb_rhs(t, y, p, out);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
+    } else if (a.kind == 1) {
+        double out[NS * NS];
+        sb_jac(t, y, p, out);
+#pragma unroll
+        for (int k = 0; k < NS * NS; ++k) a.out[i * NS * NS + k] = out[k];
+    } else if (a.kind == 2) {
+        double out[NS];
+        sb_adj_rhs(t, y, lam, p, out);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
+    } else if (a.kind == 3) {
+        double out[ND_];
+        sb_quad_rhs(t, y, lam, p, out);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) a.out[i * ND + k] = out[k];
+    }
+}
+
 }  // namespace sb
 
 #ifdef SB_FUND
@@ -808,35 +841,8 @@ sb_backward_flat(const __grid_constant__ SbBackwardArgs a) { sb_backward_body<tr
 
 extern "C" __global__ void __launch_bounds__(256)
 sb_eval(const SbEvalArgs a) {
-    using namespace sb;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    double y[NS], p[NP_], lam[NS];
-    const double t = a.t[i];
-#pragma unroll
-    for (int k = 0; k < NS; ++k) { y[k] = a.y[i * NS + k]; lam[k] = a.lam ? a.lam[i * NS + k] : 0.0; }
-#pragma unroll
-    for (int k = 0; k < NP; ++k) p[k] = a.params_shared ? a.params[k] : a.params[i * NP + k];
-    if (a.kind == 0) {
-        double out[NS];
-        sb_rhs(t, y, p, out);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
-    } else if (a.kind == 1) {
-        double out[NS * NS];
-        sb_jac(t, y, p, out);
-#pragma unroll
-        for (int k = 0; k < NS * NS; ++k) a.out[i * NS * NS + k] = out[k];
-    } else if (a.kind == 2) {
-        double out[NS];
-        sb_adj_rhs(t, y, lam, p, out);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) a.out[i * NS + k] = out[k];
-    } else if (a.kind == 3) {
-        double out[ND_];
-        sb_quad_rhs(t, y, lam, p, out);
-#pragma unroll
-        for (int k = 0; k < ND; ++k) a.out[i * ND + k] = out[k];
-    }
+    sb::eval_instance(a, i);
 }
 #endif  // SB_HOST_EMULATION

@@ -67,6 +67,9 @@ void emu_backward_group(const SbBackwardArgs* a) {
     pthread_barrier_destroy(&emu_group.bar);
 }
 #endif
+void emu_eval(const SbEvalArgs* a) {
+    for (long long i = 0; i < a->n; ++i) sb::eval_instance(*a, i);
+}
 int emu_hist_stride() { return sb::HIST_STRIDE; }   // what the cubin exports as sb_hist_stride
 int emu_sizes(int* ns, int* np, int* nd) { *ns = SB_NS; *np = SB_NP; *nd = SB_ND; return 0; }
 // sizeof the argument blocks as the C++ side sees them (checked against the ctypes mirrors)

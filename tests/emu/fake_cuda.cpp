@@ -30,7 +30,7 @@ const char* emu_symbol(const char* kernel) {
     static const char* const map[][2] = {
         {"sb_forward", "emu_forward"}, {"sb_forward_sens", "emu_forward_sens"},
         {"sb_tables", "emu_tables"}, {"sb_backward", "emu_backward"},
-        {"sb_backward_fund", "emu_backward_fund"}, {nullptr, nullptr}};
+        {"sb_backward_fund", "emu_backward_fund"}, {"sb_eval", "emu_eval"}, {nullptr, nullptr}};
     for (int i = 0; map[i][0]; ++i)
         if (!strcmp(map[i][0], kernel)) return map[i][1];
     return nullptr;
@@ -71,9 +71,9 @@ CUresult cuModuleGetFunction(CUfunction* f, CUmodule mod, const char* name) {
     FakeFunc& ff = m->funcs[m->n_funcs];
     ff.name = name;
     ff.fn = nullptr;
-    if (!strcmp(name, "sb_eval") || !strcmp(name, "sb_backward_flat")) {
-        // not emulated: sb_eval is not on the solve path; the flat build of the backward kernel
-        // computes what sb_backward computes (tests/test_gpu_parity.py), so it is a no-op here
+    if (!strcmp(name, "sb_backward_flat")) {
+        // the flat build of the backward kernel computes what sb_backward computes
+        // (tests/test_gpu_parity.py), so it is a no-op here
     } else {
         const char* sym = emu_symbol(name);
         ff.fn = sym ? (void (*)(const void*))dlsym(m->lib, sym) : nullptr;
