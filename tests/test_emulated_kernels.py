@@ -154,7 +154,7 @@ def test_lane_group_code_matches_one_lane_per_instance(tmp_path):
     integrator: same step sequence but for rounding-level flips, gradients to 1e-9."""
     w = examples.workloads()['seir_adj']
     prob = w.make_problem()
-    B = 6
+    B = 3
     y0, theta = w.draws(B)
     grads = np.random.default_rng(12).standard_normal((B, len(w.tvals), prob.n_states))
     one = None
