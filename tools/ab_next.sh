@@ -22,6 +22,9 @@ python bench.py --workload seir_adj --batch 32768 $Q > $O/ab_seir_nvrtc129.json 
 python bench.py --backward-tol 1e-8 $Q > $O/ab_lv_bwdtol1e-8.json 2> $O/ab_lv_bwdtol.err
 python bench.py --backward fundamental $Q > $O/ab_lv_fundamental.json 2> $O/ab_lv_fundamental.err
 python bench.py --interpolation hermite $Q > $O/ab_lv_hermite.json 2> $O/ab_lv_hermite.err
+ncu --set full --clock-control none --import-source on -k regex:^sb_backward_fund$ -c 1 \
+    -o $O/ncu_sb_backward_fund_lv -f \
+    python bench.py --backward fundamental --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $O/ab_ncu_fund.log 2>&1
 for f in $O/ab_*.json; do python - "$f" <<'PY'
 import json, sys
 try:
