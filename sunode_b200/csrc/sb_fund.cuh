@@ -73,6 +73,19 @@ __device__ __forceinline__ void backward_fund_instance(const SbBackwardArgs& a, 
     bdf.clear_stats();
     const double* g_base = a.grads_shared ? a.grads : a.grads + (size_t)inst * a.n_t * NS;
 
+    // optional traces (solver.py:778-781): lamda / quadrature right after the jump at the lower end
+    // of interval k < n_t, same row convention as backward_unit
+    auto trace = [&](int k, const double* lam_now) {
+        const size_t row = (size_t)inst * a.n_t + (size_t)((a.n_t - k) % a.n_t);
+        if (a.lamda_all)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) a.lamda_all[row * NS + i] = lam_now[i];
+        if (a.quad_all)
+#pragma unroll
+            for (int i = 0; i < ND; ++i) a.quad_all[row * ND + i] = quad[i];
+    };
+    const bool tracing = a.lamda_all || a.quad_all;
+
     // ts = [t_start] + reversed(tvals) + [t_end]; interval k is (ts[k+1], ts[k]) (solver.py:750-754)
     const int k_end = a.n_t + 1;
     int k = valid ? 0 : k_end;
@@ -102,9 +115,11 @@ __device__ __forceinline__ void backward_fund_instance(const SbBackwardArgs& a, 
                         break;                       // needs steps (or failed)
                     }
                     // an empty interval: only the jump (solver.py:770-776)
-                    if (g)
+                    if (g) {
 #pragma unroll
                         for (int i = 0; i < NS; ++i) lam[i] -= g[i];
+                        if (tracing) trace(k, lam);
+                    }
                 } else {
                     if (!(bdf.nst > 0 && (bdf.tn - t_lower) * bdf.h >= 0.0)) break;   // step on
                     double psi[NN];
@@ -158,8 +173,19 @@ __device__ __forceinline__ void backward_fund_instance(const SbBackwardArgs& a, 
 #pragma unroll
                             for (int i = 0; i < NS; ++i) lam[i] -= g[i];
                             nrebase++;
+                            if (tracing) trace(k, lam);
                         }
                         open = false;
+                    } else if (g && tracing) {
+                        double lam_now[NS];
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int b = 0; b < NS; ++b) s = fma(psi[b * NS + i], coef[b], s);
+                            lam_now[i] = s;
+                        }
+                        trace(k, lam_now);
                     }
                 }
                 nloc = 0;
@@ -193,6 +219,11 @@ __device__ __forceinline__ void backward_fund_instance(const SbBackwardArgs& a, 
     for (int i = 0; i < ND; ++i) gout[i] = ok ? quad[i] : qnan();
 #pragma unroll
     for (int i = 0; i < NS; ++i) lout[i] = ok ? lam[i] : qnan();
+    if (!ok && tracing) {
+        // a failed instance reads as NaN everywhere (as_pytensor.py:339-341)
+        for (int j = 0; a.lamda_all && j < a.n_t * NS; ++j) a.lamda_all[(size_t)inst * a.n_t * NS + j] = qnan();
+        for (int j = 0; a.quad_all && j < a.n_t * ND; ++j) a.quad_all[(size_t)inst * a.n_t * ND + j] = qnan();
+    }
     a.status[inst] = status;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;

@@ -534,8 +534,6 @@ class AdjointSolver(_ParamsMixin):
         ``(grad_out[B, n_deriv], lamda_out[B, n_states], status[B])``."""
         if self._last_forward is None:
             raise SolverError('solve_backward called before solve_forward.')
-        if self._backward == 'fundamental' and (lamda_all_out is not None or quad_all_out is not None):
-            raise NotImplementedError('lamda_all_out / quad_all_out need backward="reference".')
         B, n_t = self._last_forward
         tvals = np.asarray(tvals, dtype=np.float64)
         if params is not None:

@@ -89,12 +89,18 @@ np.testing.assert_array_equal(out[2], ref['lamda'])
 np.testing.assert_array_equal(sb, ref['stats'])
 assert sb[:, 0].mean() < 0.25 * ref['fwd']['stats'][:, 0].mean() * 20      # ~250 against ~1 660
 np.testing.assert_allclose(out[1], g, rtol=0, atol=1e-7 * np.abs(g).max())
-try:
-    fs.solve_forward_batch(w.t0, w.tvals, y0, theta)
-    fs.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=np.empty((B, 50, 2)))
-    raise SystemExit('traces must be refused')
-except NotImplementedError:
-    pass
+# traces of the restart-free pass against the reference schedule's (separate solver, same driver)
+fs.solve_forward_batch(w.t0, w.tvals, y0, theta)
+la, qa = np.empty((B, 50, 2)), np.empty((B, 50, 2))
+fs.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=la, quad_all_out=qa)
+emulator(prob)
+rs = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+rs.solve_forward_batch(w.t0, w.tvals, y0, theta)
+lb, qb = np.empty_like(la), np.empty_like(qa)
+rs.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=lb, quad_all_out=qb)
+assert np.isfinite(la).all() and np.isfinite(qa).all()
+assert np.max(np.abs(la - lb)) <= 1e-6 * np.abs(lb).max(), np.max(np.abs(la - lb))
+assert np.max(np.abs(qa - qb)) <= 1e-6 * np.abs(qb).max(), np.max(np.abs(qa - qb))
 print('fundamental ok')
 
 # 4. history growth: default capacity forced down, the solve is repeated with a larger store

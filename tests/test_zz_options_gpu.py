@@ -170,8 +170,14 @@ def test_fundamental_matrix_backward_pass():
     assert (sb2 == 0).all()
     np.testing.assert_array_equal(g2, g)
     np.testing.assert_array_equal(l2, lam)
-    with pytest.raises(NotImplementedError):
-        solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads,
-                                    lamda_all_out=np.empty((B, len(w.tvals), 2)))
+    # the optional traces (lamda / quadrature after every jump) against the reference schedule's
+    la, qa = np.empty((B, len(w.tvals), 2)), np.empty((B, len(w.tvals), 2))
+    solver.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=la, quad_all_out=qa)
+    plain = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    plain.solve_forward_batch(w.t0, w.tvals, y0, theta)
+    lb, qb = np.empty_like(la), np.empty_like(qa)
+    plain.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads, lamda_all_out=lb, quad_all_out=qb)
+    assert np.max(np.abs(la - lb)) <= 1e-6 * np.abs(lb).max()
+    assert np.max(np.abs(qa - qb)) <= 1e-6 * np.abs(qb).max()
     with pytest.raises(NotImplementedError):
         AdjointSolver(examples.seir(), backward='fundamental')
