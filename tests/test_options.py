@@ -261,3 +261,19 @@ def test_fundamental_matrix_backward_edge_cases(tmp_path):
         np.testing.assert_allclose(r['grad'], ref[1], rtol=0, atol=2e-7 * scale + 1e-14, err_msg=str(tv))
         np.testing.assert_allclose(r['lamda'], ref[2], rtol=0, atol=2e-7 * np.abs(ref[2]).max() + 1e-14,
                                    err_msg=str(tv))
+
+
+def test_build_options_combine(tmp_path):
+    """Hermite tables + inactive constraints + the restart-free backward pass in one build: the
+    options are independent of each other (history layout / forward integrator / backward
+    driver), the result is the Hermite oracle's to the restart-free pass's tolerance."""
+    w, prob, y0, theta, grads = _case('lv_adj', 8)
+    emu = Emulator(prob, str(tmp_path), defines=('SB_HERMITE', 'SB_FUND', constraint_define([1.0, 1.0])))
+    r = emu.adjoint(w.t0, w.tvals, y0, theta, grads, 1e-8, 1e-8, hist_cap=512, fund=True)
+    ref = Oracle(prob, rtol=1e-8, atol=1e-8, interpolation='hermite', constraints=[1.0, 1.0]).solve_adjoint(
+        w.t0, w.tvals, y0, theta, grads)
+    assert (r['status'] == 0).all() and (ref[3] == 0).all()
+    np.testing.assert_array_equal(r['fwd']['stats'][:, 0], ref[4][:, 0])
+    assert np.max(np.abs(r['grad'] - ref[1]) / np.abs(ref[1]).max(axis=0)) <= 1e-7
+    assert np.max(np.abs(r['lamda'] - ref[2]) / np.abs(ref[2]).max(axis=0)) <= 1e-7
+    assert (r['stats'][:, 0] < 0.3 * ref[4][:, 7]).all()
