@@ -130,7 +130,7 @@ int sb_solve_adjoint(sb_problem* p, int64_t B, double t0, const double* tvals, i
                      void* stream);
 
 /* Batched evaluation of the generated functions: kind 0 rhs, 1 jacobian (column-major),
- * 2 adjoint rhs, 3 quadrature rhs.  Replaces calling the numba functions from Python
+ * 2 adjoint rhs, 3 quadrature rhs, 4 adjoint jacobian -J^T (column-major).  Replaces calling the numba functions from Python
  * (/root/reference/sunode/wrappers/as_pytensor.py:160-183). */
 int sb_eval(sb_problem* p, int kind, int64_t n, const double* t, const double* y,
             const double* params, int params_shared, const double* lam, double* out, int mem,

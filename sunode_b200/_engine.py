@@ -281,11 +281,11 @@ class Engine:
     def eval(self, kind: int, t, y, params, lam, out, *, params_shared: bool = False,
              stream: Optional[int] = None) -> None:
         n = int(y.shape[0])
-        n_out = {0: self.ns, 1: self.ns * self.ns, 2: self.ns, 3: self.nd}[kind]
+        n_out = {0: self.ns, 1: self.ns * self.ns, 2: self.ns, 3: self.nd, 4: self.ns * self.ns}[kind]
         a_t = _arg(t, (n,), 't')
         a_y = _arg(y, (n, self.ns), 'y')
         a_p = _arg(params, (self.np,) if params_shared else (n, self.np), 'params')
-        a_l = _arg(lam, (n, self.ns), 'lam', optional=kind in (0, 1))
+        a_l = _arg(lam, (n, self.ns), 'lam', optional=kind in (0, 1, 4))
         a_o = _arg(out, (n, n_out), 'out', writable=True)
         mem = _mem_kind([a_t, a_y, a_p, a_l, a_o])
         _lib.check(self._lib.sb_eval(self._h, int(kind), n, a_t.ptr, a_y.ptr, a_p.ptr,

@@ -124,7 +124,7 @@ typedef struct SbEvalArgs {
     const double* y;          /* [n][NS] */
     const double* params;     /* [n][NP] or [NP] when params_shared */
     const double* lam;        /* [n][NS] or NULL */
-    double* out;              /* kind 0: [n][NS] rhs; 1: [n][NS*NS] jac; 2: [n][NS] adj; 3: [n][ND] quad */
+    double* out;              /* kind 0: [n][NS] rhs; 1: [n][NS*NS] jac; 2: [n][NS] adj; 3: [n][ND] quad; 4: [n][NS*NS] adj jac */
     long long n;
     int kind;
     int params_shared;

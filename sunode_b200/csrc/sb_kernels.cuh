@@ -683,6 +683,7 @@ __device__ __forceinline__ void backward_instance_flat(const SbBackwardArgs& a, 
 
 // ------------------------------------------------------------------------------------ eval
 // One evaluation of a generated function (sb_eval): kind 0 rhs, 1 jacobian, 2 adjoint rhs,
+// 4 adjoint Jacobian (-J^T, column-major),
 // 3 quadrature rhs.
 __device__ __forceinline__ void eval_instance(const SbEvalArgs& a, long long i) {
     double y[NS], p[NP_], lam[NS];
@@ -711,6 +712,11 @@ __device__ __forceinline__ void eval_instance(const SbEvalArgs& a, long long i) 
         sb_quad_rhs(t, y, lam, p, out);
 #pragma unroll
         for (int k = 0; k < ND; ++k) a.out[i * ND + k] = out[k];
+    } else if (a.kind == 4) {
+        double out[NS * NS];
+        sb_adj_jac(t, y, p, out);
+#pragma unroll
+        for (int k = 0; k < NS * NS; ++k) a.out[i * NS * NS + k] = out[k];
     }
 }
 

@@ -42,6 +42,21 @@ def _seir(t, y, p):
     return out
 
 
+def _helpers(t, y, p):
+    # the helper functions the reference makes available inside generated code
+    # (sunode/symode/lambdify.py:59-77, 275-352): logaddexp is differentiated wrt a state and a
+    # parameter (its fdiff works upstream); expit / dexpit / the cardinal B-spline only take the
+    # time as argument, because the reference's expit.fdiff / dexpit.fdiff raise when sympy
+    # differentiates through them (lambdify.py:301-305, 318-322) and CardinalBSpline has no fdiff
+    import sys
+    fn = sys.modules.get('sunode.symode.lambdify')          # the generator run: the reference's
+    if fn is None:
+        from sunode_b200.symode import functions as fn      # the tests: ours
+    forcing = fn.interpolate_spline(t, [p.c[0], p.c[1], p.c[2], 0.5, 0.25], 0, 3, 4)
+    return {'u': -p.k * fn.expit(t - 1) * y.u + forcing + fn.logaddexp(y.v, p.k),
+            'v': fn.dexpit(2 * t - 1) * y.u - y.v * fn.logaddexp(p.c[0], y.u)}
+
+
 _SEIR_PARAMS = ['beta1', 'beta2', 'kappa', 'sigma', 'gamma', 'omega']
 _SEIR_GROUP = {'S': (), 'E': (), 'I': (), 'R': ()}
 
@@ -55,4 +70,5 @@ CASES = {
     # appended last: the generator draws its inputs sequentially, earlier cases keep their vectors
     'seir': ({n: () for n in _SEIR_PARAMS}, {'g1': dict(_SEIR_GROUP), 'g2': dict(_SEIR_GROUP)}, _seir,
              [(n,) for n in _SEIR_PARAMS]),
+    'helpers': ({'k': (), 'c': 3}, {'u': (), 'v': ()}, _helpers, [('k',), ('c',)]),
 }
