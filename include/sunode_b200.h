@@ -129,6 +129,19 @@ int sb_solve_adjoint(sb_problem* p, int64_t B, double t0, const double* tvals, i
                      int32_t* status, int32_t* stats_fwd, int32_t* stats_bwd, int mem,
                      void* stream);
 
+/* Bounded memory (the reference's `checkpoint_n`, /root/reference/sunode/solver.py:533,588): the
+ * step history and interpolation tables of one launch take hist_cap * (12 + 7 n_states) * 8 bytes
+ * per instance; sb_solve_adjoint cuts the batch into chunks whose store fits `bytes` (0 = 4/5 of the
+ * free device memory, the default) and runs forward + backward chunk by chunk.  sb_last_chunks:
+ * how many chunks the last sb_solve_adjoint call of this handle needed. */
+int sb_set_workspace_limit(sb_problem* p, size_t bytes);
+int sb_last_chunks(sb_problem* p);
+
+/* For the instances of the last forward solve: -1, or for a failed instance the index of the output
+ * time it was integrating to -- the `time=` of the reference's error text (solver.py:516-519,
+ * 716-719).  out[B] is host memory; synchronises the device. */
+int sb_forward_fail_index(sb_problem* p, int64_t B, int32_t* out);
+
 /* Batched evaluation of the generated functions: kind 0 rhs, 1 jacobian (column-major),
  * 2 adjoint rhs, 3 quadrature rhs, 4 adjoint jacobian -J^T (column-major).  Replaces calling the numba functions from Python
  * (/root/reference/sunode/wrappers/as_pytensor.py:160-183). */

@@ -32,7 +32,9 @@ def kernel_source_hash() -> str:
     global _kernel_hash
     if _kernel_hash is None:
         h = hashlib.sha256()
-        for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh', 'sb_fund.cuh'):
+        # sb_api.cpp: the NVRTC options and the prelude sb_compile adds are part of what a cubin is
+        for name in ('sb_args.h', 'sb_bdf.cuh', 'sb_kernels.cuh', 'sb_group.cuh', 'sb_fund.cuh',
+                     'sb_api.cpp'):
             with open(os.path.join(_build.CSRC, name), 'rb') as fh:
                 h.update(fh.read())
         # the compiler is part of the key: NVRTC versions generate different code (where NVRTC
@@ -119,19 +121,25 @@ def _arg(x: Any, shape: Tuple[int, ...], name: str, dtype=np.float64, writable: 
     return _Arg(a.ctypes.data if a.size else None, False, a)
 
 
-def _mem_kind(args) -> int:
+def _mem_kind(args, device: Optional[int] = None) -> int:
     kinds = {a.device for a in args if a.ptr is not None}
     if len(kinds) > 1:
         raise ValueError('all arrays of one call must live on the same side (host or device)')
+    if kinds == {True} and device is not None:
+        # the kernels run in the primary context of the engine's device, on that device's stream
+        for a in args:
+            if a.ptr is not None and a.keep.device.index != device:
+                raise ValueError('tensor on cuda:%s passed to a solver created for cuda:%d'
+                                 % (a.keep.device.index, device))
     return _lib.SB_MEM_DEVICE if kinds == {True} else _lib.SB_MEM_HOST
 
 
-def _stream(mem: int, stream: Optional[int]) -> Optional[int]:
+def _stream(mem: int, stream: Optional[int], device: int = 0) -> Optional[int]:
     if stream is not None:
         return stream
     if mem == _lib.SB_MEM_DEVICE:
         import torch
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(device).cuda_stream
     return None
 
 
@@ -208,10 +216,10 @@ class Engine:
         a_st = _arg(status, (B,), 'status', dtype=np.int32, writable=True)
         a_stats = _arg(stats, (B, _lib.SB_STATS_PER_INSTANCE), 'stats', dtype=np.int32,
                        writable=True, optional=True)
-        mem = _mem_kind([a_y0, a_p, a_out, a_st, a_stats])
+        mem = _mem_kind([a_y0, a_p, a_out, a_st, a_stats], self.device)
         _lib.check(self._lib.sb_solve_forward(
             self._h, B, float(t0), tvals.ctypes.data, n_t, a_y0.ptr, a_p.ptr, a_out.ptr, a_st.ptr,
-            a_stats.ptr, int(bool(store_history)), mem, _stream(mem, stream)))
+            a_stats.ptr, int(bool(store_history)), mem, _stream(mem, stream, self.device)))
 
     def forward_sens(self, t0: float, tvals, y0, params, sens0, y_out, sens_out, status, stats=None,
                      *, stream: Optional[int] = None) -> None:
@@ -227,10 +235,10 @@ class Engine:
         a_st = _arg(status, (B,), 'status', dtype=np.int32, writable=True)
         a_stats = _arg(stats, (B, _lib.SB_STATS_PER_INSTANCE), 'stats', dtype=np.int32,
                        writable=True, optional=True)
-        mem = _mem_kind([a_y0, a_p, a_s0, a_out, a_so, a_st, a_stats])
+        mem = _mem_kind([a_y0, a_p, a_s0, a_out, a_so, a_st, a_stats], self.device)
         _lib.check(self._lib.sb_solve_forward_sens(
             self._h, B, float(t0), tvals.ctypes.data, n_t, a_y0.ptr, a_p.ptr, a_s0.ptr, shared,
-            a_out.ptr, a_so.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream)))
+            a_out.ptr, a_so.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream, self.device)))
 
     def backward(self, t_start: float, t_end: float, tvals, params, grads, grad_out, lamda_out,
                  status, stats=None, *, lamda_all=None, quad_all=None,
@@ -248,12 +256,12 @@ class Engine:
         a_st = _arg(status, (B,), 'status', dtype=np.int32, writable=True)
         a_stats = _arg(stats, (B, _lib.SB_STATS_PER_INSTANCE), 'stats', dtype=np.int32,
                        writable=True, optional=True)
-        mem = _mem_kind([a_p, a_g, a_go, a_lo, a_st, a_stats, a_la, a_qa])
+        mem = _mem_kind([a_p, a_g, a_go, a_lo, a_st, a_stats, a_la, a_qa], self.device)
         if a_la.ptr is not None or a_qa.ptr is not None:
             _lib.check(self._lib.sb_set_backward_trace(self._h, a_la.ptr, a_qa.ptr))
         _lib.check(self._lib.sb_solve_backward(
             self._h, B, float(t_start), float(t_end), tvals.ctypes.data, n_t, a_p.ptr, a_g.ptr,
-            shared, a_go.ptr, a_lo.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream)))
+            shared, a_go.ptr, a_lo.ptr, a_st.ptr, a_stats.ptr, mem, _stream(mem, stream, self.device)))
 
     def adjoint(self, t0: float, tvals, y0, params, grads, y_out, grad_out, lamda_out, status,
                 stats_fwd=None, stats_bwd=None, *, stream: Optional[int] = None) -> None:
@@ -272,11 +280,11 @@ class Engine:
                     writable=True, optional=True)
         a_sb = _arg(stats_bwd, (B, _lib.SB_STATS_PER_INSTANCE), 'stats_bwd', dtype=np.int32,
                     writable=True, optional=True)
-        mem = _mem_kind([a_y0, a_p, a_g, a_out, a_go, a_lo, a_st, a_sf, a_sb])
+        mem = _mem_kind([a_y0, a_p, a_g, a_out, a_go, a_lo, a_st, a_sf, a_sb], self.device)
         _lib.check(self._lib.sb_solve_adjoint(
             self._h, B, float(t0), tvals.ctypes.data, n_t, a_y0.ptr, a_p.ptr, a_g.ptr, shared,
             a_out.ptr, a_go.ptr, a_lo.ptr, a_st.ptr, a_sf.ptr, a_sb.ptr, mem,
-            _stream(mem, stream)))
+            _stream(mem, stream, self.device)))
 
     def eval(self, kind: int, t, y, params, lam, out, *, params_shared: bool = False,
              stream: Optional[int] = None) -> None:
@@ -287,10 +295,21 @@ class Engine:
         a_p = _arg(params, (self.np,) if params_shared else (n, self.np), 'params')
         a_l = _arg(lam, (n, self.ns), 'lam', optional=kind in (0, 1, 4))
         a_o = _arg(out, (n, n_out), 'out', writable=True)
-        mem = _mem_kind([a_t, a_y, a_p, a_l, a_o])
+        mem = _mem_kind([a_t, a_y, a_p, a_l, a_o], self.device)
         _lib.check(self._lib.sb_eval(self._h, int(kind), n, a_t.ptr, a_y.ptr, a_p.ptr,
                                      int(bool(params_shared)), a_l.ptr, a_o.ptr, mem,
-                                     _stream(mem, stream)))
+                                     _stream(mem, stream, self.device)))
+
+    def set_workspace_limit(self, n_bytes: int) -> None:
+        _lib.check(self._lib.sb_set_workspace_limit(self._h, int(n_bytes)))
+
+    def last_chunks(self) -> int:
+        return int(self._lib.sb_last_chunks(self._h))
+
+    def forward_fail_index(self, B: int) -> np.ndarray:
+        out = np.empty((int(B),), dtype=np.int32)
+        _lib.check(self._lib.sb_forward_fail_index(self._h, int(B), out.ctypes.data))
+        return out
 
     # ------------------------------------------------------------------ introspection
     def synchronize(self) -> None:

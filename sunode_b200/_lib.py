@@ -68,6 +68,9 @@ def _declare(lib: ctypes.CDLL) -> None:
                                       _VP, _VP, _VP, _VP, c_int, _VP]),
         'sb_solve_adjoint': (c_int, [_VP, c_i64, c_double, _VP, c_int, _VP, _VP, _VP, c_int,
                                      _VP, _VP, _VP, _VP, _VP, _VP, c_int, _VP]),
+        'sb_set_workspace_limit': (c_int, [_VP, c_size]),
+        'sb_last_chunks': (c_int, [_VP]),
+        'sb_forward_fail_index': (c_int, [_VP, c_i64, _VP]),
         'sb_eval': (c_int, [_VP, c_int, c_i64, _VP, _VP, _VP, c_int, _VP, _VP, c_int, _VP]),
         'sb_synchronize': (c_int, [_VP]),
         'sb_last_kernel_ms': (c_int, [_VP] + [ctypes.POINTER(ctypes.c_float)] * 3),
@@ -87,7 +90,7 @@ EXPORTS = (
     'sb_problem_create', 'sb_problem_destroy', 'sb_set_tolerances', 'sb_set_tolerances_b',
     'sb_set_sens_scaling', 'sb_set_quad_tolerances_b', 'sb_set_max_num_steps', 'sb_set_max_num_steps_b',
     'sb_set_history_capacity', 'sb_set_backward_trace', 'sb_solve_forward', 'sb_solve_forward_sens', 'sb_solve_backward',
-    'sb_solve_adjoint',
+    'sb_solve_adjoint', 'sb_set_workspace_limit', 'sb_last_chunks', 'sb_forward_fail_index',
     'sb_eval', 'sb_synchronize', 'sb_last_kernel_ms', 'sb_launch_count', 'sb_kernel_info',
     'sb_host_alloc', 'sb_host_free',
 )
@@ -101,10 +104,14 @@ def lib() -> ctypes.CDLL:
         if _build.needs_build():
             try:
                 path = _build.build_library()
-            except Exception as err:  # noqa: BLE001 - reported, not swallowed
+            except Exception as err:  # noqa: BLE001
                 if not os.path.exists(path):
                     raise ImportError(
                         'libsunode_b200.so is missing and could not be built: %s' % err) from err
+                # a stale library embeds OLD kernel sources: say so instead of running them silently
+                import warnings
+                warnings.warn('libsunode_b200.so is older than its sources and the rebuild failed '
+                              '(%s); the stale library is used' % err, RuntimeWarning, stacklevel=2)
         handle = ctypes.CDLL(path)
         _declare(handle)
         _lib = handle

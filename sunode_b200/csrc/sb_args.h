@@ -62,6 +62,9 @@ typedef struct SbForwardArgs {
     /* when set: the accepted steps of all successful instances are added up here; the backward
      * kernels choose their interval schedule from it (see SbBackwardArgs.steps_total) */
     unsigned long long* steps_total;
+    /* when set: -1, or for a failed instance the index of the output time it was integrating to
+     * (the `time=` of the reference's error message, solver.py:516-519) */
+    int* fail_k;              /* [B] or NULL */
 } SbForwardArgs;
 
 typedef struct SbTablesArgs {

@@ -292,6 +292,7 @@ __device__ __forceinline__ void forward_instance_t(const SbForwardArgs& a, long 
         if (NBLK > 1) for (int j = 0; j < a.n_t * (NT - NS); ++j) so[j] = qnan();
     }
     a.status[inst] = status;
+    if (a.fail_k) a.fail_k[inst] = (status == SB_SUCCESS) ? -1 : min(k, a.n_t - 1);
     if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? bdf.nst + 1 : 0;
     if (a.stats) {
         int* s = a.stats + inst * SB_STATS_STRIDE;

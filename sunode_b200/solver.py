@@ -127,11 +127,10 @@ class _ParamsMixin:
         return y0
 
 
-def _raise_forward(status: int, tvals, y_row) -> None:
-    """Reproduce the reference's error text (solver.py:516-519, 716-719)."""
-    finite = np.isfinite(np.asarray(y_row)).all(axis=-1) if len(tvals) else np.zeros(0, bool)
-    t_fail = tvals[int(np.argmin(finite))] if len(tvals) and not finite.all() else (
-        tvals[-1] if len(tvals) else float('nan'))
+def _raise_forward(status: int, tvals, fail_k: int) -> None:
+    """Reproduce the reference's error text (solver.py:516-519, 716-719): ``time`` is the output
+    time the integrator was heading for (``fail_k`` from the forward kernel)."""
+    t_fail = tvals[fail_k] if 0 <= fail_k < len(tvals) else (tvals[-1] if len(tvals) else float('nan'))
     if status == CV_TOO_MUCH_WORK:
         raise SolverError(f"Too many solver retries before time={t_fail}.")
     error = ERRORS.get(int(status), 'UNKNOWN')
@@ -279,13 +278,13 @@ class Solver(_ParamsMixin):
             out, sens, status = self.solve_sens_batch(t0, tvals, y0[None, :], None, sens0,
                                                       max_retries=max_retries)
             if status[0] != 0:
-                _raise_forward(int(status[0]), tvals, out[0])
+                _raise_forward(int(status[0]), tvals, int(self._engine.forward_fail_index(1)[0]))
             y_out[...] = out[0]
             sens_out[...] = sens[0]
             return
         out, status = self.solve_batch(t0, tvals, y0[None, :], None, max_retries=max_retries)
         if status[0] != 0:
-            _raise_forward(int(status[0]), tvals, out[0])
+            _raise_forward(int(status[0]), tvals, int(self._engine.forward_fail_index(1)[0]))
         y_out[...] = out[0]
 
     # ------------------------------------------------------------------ batched
@@ -443,6 +442,13 @@ class AdjointSolver(_ParamsMixin):
         self._history_auto = False
         self._engine.set_history_capacity(self._history_capacity)
 
+    def set_workspace_limit(self, n_bytes: int) -> None:
+        """Upper bound in bytes for the step history + interpolation tables of one launch (default:
+        4/5 of the free device memory).  :meth:`solve_adjoint_batch` cuts a batch whose store would
+        not fit into chunks and runs forward + backward chunk by chunk -- the bounded-memory
+        counterpart of the reference's ``checkpoint_n`` (solver.py:533,588)."""
+        self._engine.set_workspace_limit(int(n_bytes))
+
     _HISTORY_BYTES_MAX = 32 << 30
 
     def _grow_history(self, B: int, status, stats) -> bool:
@@ -477,7 +483,7 @@ class AdjointSolver(_ParamsMixin):
         tvals = np.asarray(tvals, dtype=np.float64)
         out, status = self.solve_forward_batch(t0, tvals, y0, None, max_retries=max_retries)
         if status[0] != 0:
-            _raise_forward(int(status[0]), tvals, out[0])
+            _raise_forward(int(status[0]), tvals, int(self._engine.forward_fail_index(1)[0]))
         y_out[...] = out[0]
 
     def solve_backward(self, t0, tend, tvals, grads, grad_out, lamda_out,

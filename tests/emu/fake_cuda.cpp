@@ -106,6 +106,10 @@ CUresult cuMemAlloc(CUdeviceptr* p, size_t bytes) {
     return CUDA_SUCCESS;
 }
 CUresult cuMemFree(CUdeviceptr p) { free((void*)p); return CUDA_SUCCESS; }
+CUresult cuMemGetInfo(size_t* free_b, size_t* total_b) {
+    *free_b = (size_t)8 << 30; *total_b = (size_t)16 << 30;
+    return CUDA_SUCCESS;
+}
 CUresult cuMemHostAlloc(void** p, size_t bytes, unsigned) { *p = malloc(bytes ? bytes : 1); return *p ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY; }
 CUresult cuMemFreeHost(void* p) { free(p); return CUDA_SUCCESS; }
 CUresult cuMemcpyDtoH(void* d, CUdeviceptr s, size_t n) { memcpy(d, (const void*)s, n); return CUDA_SUCCESS; }

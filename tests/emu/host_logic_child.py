@@ -143,4 +143,67 @@ for cons in ([0.0, 1.0], [2.0, 1.0]):
     np.testing.assert_array_equal(stc, ref['status'])
     np.testing.assert_array_equal(yc, ref['y'])
 print('constraints ok')
+
+# 7. bounded memory: a workspace limit below the batch's store cuts sb_solve_adjoint into chunks
+#    (forward + backward chunk by chunk); results are those of the single launch, bit for bit
+emulator(prob)
+cs = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+per_instance = 512 * ((2 + 2) + (10 + 6 * 2)) * 8
+cs.set_workspace_limit(9 * per_instance)                 # 40 draws -> chunks of 9
+la, qa = np.empty((B, 50, 2)), np.empty((B, 50, 2))
+sfc, sbc = np.zeros((B, 8), np.int32), np.zeros((B, 8), np.int32)
+yc, gc, lc, stc = cs.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, stats_fwd=sfc, stats_bwd=sbc)
+assert cs._engine.last_chunks() == 5, cs._engine.last_chunks()
+for a, b in ((yc, y), (gc, g), (lc, lam), (stc, np.zeros(B, np.int32)), (sfc, sf)):
+    np.testing.assert_array_equal(a, b)
+gs = np.ones((len(w.tvals), 2))                          # shared cotangent through the chunk loop
+g_one = solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, gs)[1]
+np.testing.assert_array_equal(cs.solve_adjoint_batch(w.t0, w.tvals, y0, theta, gs)[1], g_one)
+try:                                                     # the chunked store holds the last chunk only
+    cs.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)
+    raise AssertionError('solve_backward after a chunked solve_adjoint must be refused')
+except _lib.LibraryError as err:
+    assert 'stored forward solve' in str(err)
+cs.set_workspace_limit(per_instance // 2)
+try:
+    cs.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    raise AssertionError('a store that cannot hold one instance must be refused')
+except _lib.LibraryError as err:
+    assert 'workspace limit' in str(err)
+print('chunking ok')
+
+# 8. the reference's error text names the output time that was being integrated to
+from sunode_b200 import SympyProblem                      # noqa: E402
+from sunode_b200.basic import SolverError                 # noqa: E402
+bprob = SympyProblem({'k': ()}, {'x': ()}, lambda t, y, p: {'x': p.k * y.x ** 2}, [('k',)])
+emulator(bprob)
+bs = Solver(bprob, abstol=1e-8, reltol=1e-8)
+btv = np.linspace(0.1, 2, 20)
+bs.set_params(np.array((1.0,), dtype=bprob.params_dtype)[()])      # x = 1 / (1 - t): blows up at t = 1
+try:
+    bs.solve(0.0, btv, np.ones(1), bs.make_output_buffers(btv))
+    raise AssertionError('expected SolverError')
+except SolverError as err:
+    assert 'before time=%s' % btv[9] in str(err), str(err)      # 0.1 + 9 * 0.1, just short of the pole
+print('failing time ok')
+
+# 9. armed traces are dropped by a call that fails validation; parameters of the stored forward
+#    pass are the handle's own copy
+emulator(prob)
+ts = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+th = theta.copy()
+ts.solve_forward_batch(w.t0, w.tvals, y0, th)
+th[...] = np.nan                                          # the caller's array dies / is overwritten
+la = np.full((B, 50, 2), 7.0)
+try:                                                      # wrong n_t: refused before any launch
+    ts._engine.backward(w.tvals[-1], w.t0, w.tvals[:-1], None, grads[:, :-1], np.empty((B, 2)),
+                        np.empty((B, 2)), np.empty(B, np.int32), lamda_all=la[:, :-1].copy())
+    raise AssertionError('expected a state error')
+except _lib.LibraryError:
+    pass
+g9, l9, st9 = ts.solve_backward_batch(w.tvals[-1], w.t0, w.tvals, grads)   # no trace requested
+assert (st9 == 0).all() and (la == 7.0).all()
+np.testing.assert_array_equal(g9, g)
+np.testing.assert_array_equal(l9, lam)
+print('trace / params lifetime ok')
 print('ALL OK')

@@ -36,8 +36,21 @@ class _EmuSolver:
                              1e-8, 1e-8, hist_cap=512)
         return r['y'], r['grad'], r['lamda'], r['status']
 
+    # the split calls (what the overlapped path of sharding.solve_adjoint_gathered uses)
+    def solve_forward_batch(self, t0, tvals, y0, params, y_out=None):
+        self._fwd = (t0, np.asarray(y0), np.asarray(params))
+        r = self.emu.forward(t0, tvals, np.asarray(y0), np.asarray(params), 1e-8, 1e-8)
+        return r['y'], r['status']
 
-def _worker(rank, world, port, tmpdir, B):
+    def solve_backward_batch(self, t_last, t_first, tvals, grads, grad_out=None, lamda_out=None,
+                             status=None):
+        t0, y0, params = self._fwd
+        assert t_first == t0 and t_last == tvals[-1]
+        r = self.emu.adjoint(t0, tvals, y0, params, np.asarray(grads), 1e-8, 1e-8, hist_cap=512)
+        return r['grad'], r['lamda'], r['status']
+
+
+def _worker(rank, world, port, tmpdir, B, overlap):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from sunode_b200 import examples
@@ -51,14 +64,17 @@ def _worker(rank, world, port, tmpdir, B):
         rng = np.random.default_rng(5)
         grads = rng.standard_normal((B, len(w.tvals), prob.n_states))
         solver = _EmuSolver(prob, os.path.join(tmpdir, 'emu%d' % rank))
-        y, g, lam, st = solve_adjoint_sharded(solver, w.t0, w.tvals, y0, theta, grads)
+        y, g, lam, st = solve_adjoint_sharded(solver, w.t0, w.tvals, y0, theta, grads,
+                                              overlap=overlap)
         np.savez(os.path.join(tmpdir, 'out%d.npz' % rank), y=y, g=g, lam=lam, st=st)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('B', [37, 64])
-def test_two_rank_gloo_equals_single_process(tmp_path, B):
+@pytest.mark.parametrize('B,overlap', [(37, False), (64, True), (37, True)])
+def test_two_rank_gloo_equals_single_process(tmp_path, B, overlap):
+    """``overlap``: forward, trajectories' all-gather in flight (async), backward, small gather --
+    the order the GPU path uses to hide the collective under the backward kernels."""
     import socket
     import torch.multiprocessing as mp
     from sunode_b200 import examples
@@ -66,7 +82,7 @@ def test_two_rank_gloo_equals_single_process(tmp_path, B):
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), B), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), B, overlap), nprocs=2, join=True)
 
     w = examples.workloads()['lv_adj']
     prob = w.make_problem()
