@@ -291,13 +291,13 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
         small_all = torch.empty((world * B, n_d + n_s + 1), dtype=torch.float64, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def device_step(y0, theta, grads, stats=False):
+    def device_step(y0, theta, grads, stats=False, host_out=None):
         """The hot path on device-resident arrays.  N > 1: through sunode_b200.sharding -- the
         trajectories' all-gather is in flight underneath the backward kernels."""
         if w.adjoint and gather and not stats:
             sharding.solve_adjoint_gathered(solver, w.t0, w.tvals, y0, theta, grads, counts,
                                             y_out=y_d, grad_out=g_d, lamda_out=l_d, status=st_d,
-                                            y_all=y_all, small_all=small_all)
+                                            y_all=y_all, small_all=small_all, host_out=host_out)
         elif w.adjoint:
             solver.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads, y_out=y_d,
                                        grad_out=g_d, lamda_out=l_d, status=st_d,
@@ -308,6 +308,9 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
                                stats=sf_d if stats else None)
             if gather:
                 dist.all_gather_into_tensor(y_all, y_d)
+            if host_out is not None:
+                host_out['y'].copy_(y_d, non_blocking=True)
+                host_out['st'].copy_(st_d, non_blocking=True)
 
     for i in range(max(warmup, 1)):
         device_step(y0_d, theta_d, grads_d, stats=(i == 0))
@@ -380,16 +383,12 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
             tp = {k: torch.from_numpy(v.array) for k, v in pin.items()}
             tp_st = torch.from_numpy(pin_st.array)
             in_d = {k: torch.empty_like(tp[k], device=dev) for k in ('y0', 'theta', 'grads')}
+            host = {'y': tp['y'], 'g': tp['g'], 'l': tp['l'], 'st': tp_st}
 
             def e2e_step():
                 for k in ('y0', 'theta', 'grads'):
                     in_d[k].copy_(tp[k], non_blocking=True)
-                device_step(in_d['y0'], in_d['theta'], in_d['grads'])
-                tp['y'].copy_(y_d, non_blocking=True)
-                if w.adjoint:
-                    tp['g'].copy_(g_d, non_blocking=True)
-                    tp['l'].copy_(l_d, non_blocking=True)
-                tp_st.copy_(st_d, non_blocking=True)
+                device_step(in_d['y0'], in_d['theta'], in_d['grads'], host_out=host)
                 torch.cuda.current_stream().synchronize()
             api = ('pinned host shard -> device (torch copies), sunode_b200.sharding.solve_adjoint_gathered '
                    '(all-gathers included), this rank\'s results -> pinned host')

@@ -541,6 +541,9 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
                 }
                 int nloc = 0;
                 bool reached = false;
+#ifdef SB_REJOIN
+                bool sat_out = false;
+#endif
                 for (;;) {
                     bool work = valid && status == SB_SUCCESS && !reached;
                     if (work && !bdf.in_step) {
@@ -548,6 +551,26 @@ __device__ __forceinline__ void backward_unit(const SbBackwardArgs& a, long long
                         else status = bdf.pre_step_checks(sys);
                         work = status == SB_SUCCESS;
                     }
+#ifdef SB_REJOIN
+                    {
+                        // Order selection (three step-size roots, two extra norms: a quarter of a
+                        // pass) runs at the end of a step entered with qwait == 1 -- at constant
+                        // order every other step, so the lanes of a warp fall into two classes and
+                        // the block runs in every pass for about half of them.  A lane of the
+                        // smaller class sits one pass out when that class is small (SB_REJOIN 32nds
+                        // of the working lanes); after it, its countdown matches the majority's.
+                        // Lanes wait for the slowest lane of the interval anyway; the per-lane
+                        // sequence of operations, hence every result, is unchanged.
+                        const bool sel = work && bdf.qwait == 1 && bdf.etamax != 1.0;
+                        const unsigned m_work = sb_ballot(work), m_sel = sb_ballot(sel);
+                        const int n_work = __popc(m_work), n_sel = __popc(m_sel);
+                        const bool minority = (2 * n_sel <= n_work) ? sel : !sel;
+                        const int n_min = (2 * n_sel <= n_work) ? n_sel : n_work - n_sel;
+                        const bool sit = work && minority && !sat_out && n_min > 0 && 32 * n_min <= SB_REJOIN * n_work;
+                        sat_out = sit;
+                        if (sit) work = false;
+                    }
+#endif
                     const unsigned mask = sb_ballot(work);
                     if (mask == 0u) break;
                     if (work) {

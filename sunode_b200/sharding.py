@@ -55,16 +55,32 @@ class _Gather:
                           for r, c in enumerate(self.counts)], dim=0)
 
 
+_copy_streams: dict = {}
+
+
+def _copy_stream(device):
+    import torch
+    key = torch.device(device).index
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
 def solve_adjoint_gathered(solver: Any, t0: float, tvals, y0, params, grads, counts: List[int], *,
                            group: Optional[Any] = None, y_out=None, grad_out=None, lamda_out=None,
-                           status=None, y_all=None, small_all=None, overlap: Optional[bool] = None):
+                           status=None, y_all=None, small_all=None, overlap: Optional[bool] = None,
+                           host_out: Optional[dict] = None):
     """This rank's shard (``y0[B_r, n_s]`` ...) solved forward + adjoint, results of ALL ranks
     returned: ``(y_all, grad_all, lamda_all, status_all)``; ``counts[r]`` = instances of rank r.
 
     ``overlap`` (default: whenever the solver offers the split calls and the shard lives on a
     GPU): forward pass, then the trajectories' all-gather asynchronously, then the backward pass,
     so that the collective runs underneath the backward kernels.  Otherwise one fused
-    ``solve_adjoint_batch`` followed by both gathers.  Results are identical either way."""
+    ``solve_adjoint_batch`` followed by both gathers.  Results are identical either way.
+
+    ``host_out`` (overlapped path only): pinned CPU tensors ``{'y', 'g', 'l', 'st'}`` that receive
+    this rank's OWN results; the trajectories' download runs on a copy stream underneath the
+    backward kernels too.  The caller synchronises the current stream before reading them."""
     import numpy as np
     import torch
 
@@ -79,8 +95,19 @@ def solve_adjoint_gathered(solver: Any, t0: float, tvals, y0, params, grads, cou
     if overlap:
         y, st_f = solver.solve_forward_batch(t0, tvals, y0, params, y_out=y_out)
         pending_y = _Gather(tensor(y), counts, group, out=y_all)         # travels under the backward pass
+        if host_out is not None:
+            main = torch.cuda.current_stream(y.device)
+            side = _copy_stream(y.device)
+            side.wait_stream(main)                                       # y is final after the forward kernel
+            with torch.cuda.stream(side):
+                host_out['y'].copy_(y, non_blocking=True)
         g, lam, status = solver.solve_backward_batch(tvals[-1], t0, tvals, grads, grad_out=grad_out,
                                                      lamda_out=lamda_out, status=status)
+        if host_out is not None:
+            host_out['g'].copy_(g, non_blocking=True)
+            host_out['l'].copy_(lam, non_blocking=True)
+            host_out['st'].copy_(status, non_blocking=True)
+            main.wait_stream(side)
     else:
         kw = {}
         if y_out is not None:

@@ -24,7 +24,7 @@ class ForwardArgs(ctypes.Structure):
                 ('params', _DP), ('atol', _DP), ('y_out', _DP), ('hist', _DP), ('hist_n', _IP),
                 ('status', _IP), ('stats', _IP), ('B', ctypes.c_longlong), ('n_t', ctypes.c_int),
                 ('hist_cap', ctypes.c_int), ('max_steps', ctypes.c_int),
-                ('sens0_shared', ctypes.c_int), ('lanes', ctypes.c_int), ('pad_', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP), ('tab', _DP), ('steps_total', ctypes.c_void_p)]
+                ('sens0_shared', ctypes.c_int), ('lanes', ctypes.c_int), ('pad_', ctypes.c_int), ('sens0', _DP), ('sens_out', _DP), ('tab', _DP), ('steps_total', ctypes.c_void_p), ('fail_k', _IP)]
 
 
 class TablesArgs(ctypes.Structure):
