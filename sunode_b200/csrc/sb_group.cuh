@@ -160,14 +160,24 @@ struct LaneGroup {
         double v[C], x[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { mystep[c] = (int)m[C * N_ + c]; v[c] = b[c]; x[c] = 0.0; }
+        // (both sweeps rolled by default: the grouped kernel is instruction-fetch bound -- ncu: 43 %
+        // of the stall samples are no_inst -- and unrolled they were 955 of its 7 700 instructions)
+#ifdef SB_GROUP_UNROLL_SOLVE
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
         for (int k = 0; k < N_; ++k) {             // L y = P b
             const int p = piv[k], pl = p / C, pc = p - pl * C;
             const double vk = __shfl_sync(gm, pick<C>(v, pc), pl, G);
 #pragma unroll
             for (int c = 0; c < C; ++c) v[c] = (mystep[c] > k) ? fma(-m[c * N_ + k], vk, v[c]) : v[c];
         }
+#ifdef SB_GROUP_UNROLL_SOLVE
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
         for (int k = N_ - 1; k >= 0; --k) {        // U x = y
             const int p = piv[k], pl = p / C, pc = p - pl * C;
             double mine = 0.0;

@@ -87,14 +87,15 @@ using FwdSys = FwdSysT<1>;
 // through the `order + 1` stored points ending at the interval's right end, scaled by the interval
 // length as CVODES does (CVApolynomialGetY); `order` is the BDF order of the step that produced
 // the right end point.  `hist` / `tab` are this instance's arrays.
+template <int OUT_STRIDE = TAB_STRIDE>
 __device__ __forceinline__ void build_table_entry_at(const double* hist, double* tab, int idx) {
-    double* e = tab + (size_t)idx * TAB_STRIDE;
+    double* e = tab + (long long)idx * OUT_STRIDE;
 #ifdef SB_HERMITE
     // CVAhermiteGetY: the cubic through (y, y') at both ends of the interval, as a Newton form
     // with the nodes t_hi, t_hi, t_lo (scaled by powers of the interval length like the
     // polynomial entries, so the backward kernels evaluate it unchanged as an order-3 entry)
     {
-        const double* p1 = hist + (size_t)idx * HIST_STRIDE;
+        const double* p1 = hist + (long long)idx * HIST_STRIDE;
         const double* p0 = p1 - HIST_STRIDE;
         const double t1 = p1[0], t0 = p0[0];
         const double D = t1 - t0, a = fabs(D);
@@ -114,14 +115,14 @@ __device__ __forceinline__ void build_table_entry_at(const double* hist, double*
         }
     }
 #else
-    int order = (int)hist[(size_t)idx * HIST_STRIDE + 1];
+    int order = (int)hist[(long long)idx * HIST_STRIDE + 1];
     if (order > idx) order = idx;
     if (order < 1) order = 1;
     double T[SB_LMAX], Y[SB_LMAX][NS];
 #pragma unroll
     for (int j = 0; j < SB_LMAX; ++j) {
         if (j <= order) {
-            const double* pnt = hist + (size_t)(idx - j) * HIST_STRIDE;
+            const double* pnt = hist + (long long)(idx - j) * HIST_STRIDE;
             T[j] = pnt[0];
 #pragma unroll
             for (int k = 0; k < NS; ++k) Y[j][k] = pnt[2 + k];
@@ -786,12 +787,57 @@ sb_backward_fund(const __grid_constant__ SbBackwardArgs a) {
 }
 #endif
 
-extern "C" __global__ void __launch_bounds__(256)
+// sb_tables: one warp builds 32 consecutive table entries of one instance.  The stored points it
+// needs (the tile's own and the SB_QMAX before it) are read with coalesced loads into shared memory,
+// every lane builds its entry there, and the tile -- 32 entries are one contiguous run of the
+// table -- goes out with coalesced stores (a lane writing its 176-byte entry by itself reached a
+// quarter of the copy bandwidth).  SB_TAB_TILES warps per instance, each walking the tiles
+// t, t + SB_TAB_TILES, ... up to the instance's stored step count: the grid does not depend on the
+// history capacity.  Entries are bit-identical to build_table_entry's (same function).
+#ifndef SB_TAB_TILES
+#define SB_TAB_TILES 4
+#endif
+#define SB_TAB_WARPS 2
+namespace sb {
+constexpr int TAB_PAD = TAB_STRIDE | 1;                         // odd stride: conflict-free
+constexpr int TAB_HIST_PTS = 32 + SB_QMAX;
+constexpr bool TAB_STAGED = (32 * TAB_PAD + TAB_HIST_PTS * HIST_STRIDE) * 8 * SB_TAB_WARPS <= 40 * 1024;
+}
+extern "C" __global__ void __launch_bounds__(32 * SB_TAB_WARPS)
 sb_tables(const SbTablesArgs a) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long inst = gid / a.hist_cap;
-    const int idx = (int)(gid - inst * a.hist_cap);
-    if (inst < a.B) sb::build_table_entry(a, inst, idx);
+    using namespace sb;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long w = (long long)blockIdx.x * SB_TAB_WARPS + wib;
+    const long long inst = w / SB_TAB_TILES;
+    if (inst >= a.B) return;
+    const int np = a.hist_n[inst];
+    const double* hist = a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE;
+    double* tab = a.tab + (size_t)inst * a.hist_cap * TAB_STRIDE;
+    if constexpr (TAB_STAGED) {
+        __shared__ double s_out[SB_TAB_WARPS][32 * TAB_PAD];
+        __shared__ double s_hist[SB_TAB_WARPS][TAB_HIST_PTS * HIST_STRIDE];
+        for (int tile = (int)(w - inst * SB_TAB_TILES); tile * 32 < np; tile += SB_TAB_TILES) {
+            const int i0 = tile * 32;                            // entries i0 .. i0 + 31
+            const int p0 = max(i0 - SB_QMAX, 0), p1 = min(i0 + 32, np);     // stored points needed
+            for (int j = lane; j < (p1 - p0) * HIST_STRIDE; j += 32)
+                s_hist[wib][j] = hist[(size_t)p0 * HIST_STRIDE + j];
+            __syncwarp();
+            const int idx = i0 + lane;
+            if (idx >= 1 && idx < np)
+                build_table_entry_at<TAB_PAD>(s_hist[wib] - (long long)p0 * HIST_STRIDE,
+                                              s_out[wib] - (long long)i0 * TAB_PAD, idx);
+            __syncwarp();
+            const int e0 = max(i0, 1), e1 = min(i0 + 32, np);    // entries to write
+            for (int j = lane; j < (e1 - e0) * TAB_STRIDE; j += 32) {
+                const int e = j / TAB_STRIDE, k = j - e * TAB_STRIDE;
+                tab[(size_t)e0 * TAB_STRIDE + j] = s_out[wib][(e0 - i0 + e) * TAB_PAD + k];
+            }
+            __syncwarp();
+        }
+    } else {
+        for (int idx = (int)(w - inst * SB_TAB_TILES) * 32 + lane; idx < np; idx += 32 * SB_TAB_TILES)
+            if (idx >= 1) build_table_entry_at(hist, tab, idx);
+    }
 }
 
 template <bool FLAT>
