@@ -69,10 +69,13 @@ def parse_args():
     return ap.parse_args()
 
 
-def algorithmic_bytes_per_solve(n_s, n_all, n_deriv, n_t, adjoint, mean_fwd_steps):
+def algorithmic_bytes_per_solve(n_s, n_all, n_deriv, n_t, adjoint, mean_fwd_steps, sens=False):
     """I/O of one solve plus, for the adjoint, every accepted forward step's
-    (t, order, y) written once and read once."""
+    (t, order, y) written once and read once; with forward sensitivities the initial and the
+    output sensitivities."""
     b = 8 * (n_s + n_all) + 8 * n_t * n_s
+    if sens:
+        b += 8 * n_deriv * n_s * (n_t + 1)
     if adjoint:
         b += 8 * n_t * n_s + 8 * (n_deriv + n_s) + 2 * 8 * mean_fwd_steps * (n_s + 2)
     return float(b)
@@ -158,6 +161,9 @@ def cpu_baseline(w, problem, n_sample, adjoint, threads=0, repeats=1):
         t = time.perf_counter()
         if adjoint:
             orc.solve_adjoint(w.t0, w.tvals, y0, theta, grads, n_threads=cores)
+        elif w.sens:
+            orc.solve_forward_sens(w.t0, w.tvals, y0, theta, np.zeros((problem.n_params, problem.n_states)),
+                                   n_threads=cores)
         else:
             orc.solve_forward(w.t0, w.tvals, y0, theta, n_threads=cores)
         dt = time.perf_counter() - t
@@ -230,7 +236,8 @@ def config_dict(w, problem, batch, n_gpus, extra=None):
 
 # (workload, draws per GPU, backward schedule) measured after the headline
 SECONDARY = [('lv_fwd', None, 'reference'), ('robertson_adj', None, 'reference'),
-             ('seir_adj', 32768, 'reference'), ('lv_adj', None, 'fundamental')]
+             ('seir_adj', 32768, 'reference'), ('lv_adj', None, 'fundamental'),
+             ('lv_fsa', None, 'reference')]
 
 
 def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_rank,
@@ -267,6 +274,7 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
             solver.set_quad_tolerances(BACKWARD_TOL, BACKWARD_TOL)
     else:
         solver = Solver(problem, abstol=1e-8, reltol=1e-8, device=local_rank,
+                        sens_mode='simultaneous' if w.sens else None,
                         block_threads=args.block, min_blocks=args.min_blocks)
     eng = solver._engine
     # JIT / codegen are excluded from the metric and reported separately
@@ -284,6 +292,9 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
     st_d = torch.empty((B,), dtype=torch.int32, device=dev)
     sf_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)
     sb_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    if w.sens:
+        s0_d = torch.zeros((n_d, n_s), dtype=torch.float64, device=dev)      # dy0/dp = 0: y0 is fixed
+        s_d = torch.empty((B, n_t, n_d, n_s), dtype=torch.float64, device=dev)
     gather = world > 1 and not args.no_gather
     counts = [B] * world
     if gather:
@@ -304,12 +315,18 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
                                        stats_fwd=sf_d if stats else None,
                                        stats_bwd=sb_d if stats else None)
         else:
-            solver.solve_batch(w.t0, w.tvals, y0, theta, y_out=y_d, status=st_d,
-                               stats=sf_d if stats else None)
+            if w.sens:
+                solver.solve_sens_batch(w.t0, w.tvals, y0, theta, s0_d, y_out=y_d, sens_out=s_d,
+                                        status=st_d, stats=sf_d if stats else None)
+            else:
+                solver.solve_batch(w.t0, w.tvals, y0, theta, y_out=y_d, status=st_d,
+                                   stats=sf_d if stats else None)
             if gather:
                 dist.all_gather_into_tensor(y_all, y_d)
             if host_out is not None:
                 host_out['y'].copy_(y_d, non_blocking=True)
+                if w.sens:
+                    host_out['s'].copy_(s_d, non_blocking=True)
                 host_out['st'].copy_(st_d, non_blocking=True)
 
     for i in range(max(warmup, 1)):
@@ -357,9 +374,14 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
     if with_e2e:
         h2d = 8 * (B * n_s + B * n_all + n_t) + (8 * n_t * n_s if w.adjoint else 0) + 8 * n_s
         d2h = 8 * B * n_t * n_s + 4 * B + (8 * B * (n_d + n_s) if w.adjoint else 0)
-        pin = {k: PinnedBuffer(s) for k, s in {
-            'y0': (B, n_s), 'theta': (B, n_all), 'grads': (n_t, n_s), 'y': (B, n_t, n_s),
-            'g': (B, n_d), 'l': (B, n_s)}.items()}
+        shapes = {'y0': (B, n_s), 'theta': (B, n_all), 'grads': (n_t, n_s), 'y': (B, n_t, n_s),
+                  'g': (B, n_d), 'l': (B, n_s)}
+        if w.sens:
+            shapes['s'] = (B, n_t, n_d, n_s)
+            s0_h = np.zeros((n_d, n_s))
+            h2d += 8 * n_d * n_s
+            d2h += 8 * B * n_t * n_d * n_s
+        pin = {k: PinnedBuffer(s) for k, s in shapes.items()}
         pin_st = PinnedBuffer((B,), np.int32)
         pin['y0'].array[...] = y0_h
         pin['theta'].array[...] = theta_h
@@ -374,6 +396,9 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
                 solver.solve_adjoint_batch(w.t0, w.tvals, buf['y0'], buf['theta'], buf['grads'],
                                            y_out=buf['y'], grad_out=buf['g'], lamda_out=buf['l'],
                                            status=st)
+            elif w.sens:
+                solver.solve_sens_batch(w.t0, w.tvals, buf['y0'], buf['theta'], s0_h, y_out=buf['y'],
+                                        sens_out=buf['s'], status=st)
             else:
                 solver.solve_batch(w.t0, w.tvals, buf['y0'], buf['theta'], y_out=buf['y'], status=st)
 
@@ -383,7 +408,7 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
             tp = {k: torch.from_numpy(v.array) for k, v in pin.items()}
             tp_st = torch.from_numpy(pin_st.array)
             in_d = {k: torch.empty_like(tp[k], device=dev) for k in ('y0', 'theta', 'grads')}
-            host = {'y': tp['y'], 'g': tp['g'], 'l': tp['l'], 'st': tp_st}
+            host = {'y': tp['y'], 'g': tp['g'], 'l': tp['l'], 'st': tp_st, 's': tp.get('s')}
 
             def e2e_step():
                 for k in ('y0', 'theta', 'grads'):
@@ -440,7 +465,7 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
                 peaks = json.load(fh)
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650'
-        bytes_solve = algorithmic_bytes_per_solve(n_s, n_all, n_d, n_t, w.adjoint, mean_fwd_steps)
+        bytes_solve = algorithmic_bytes_per_solve(n_s, n_all, n_d, n_t, w.adjoint, mean_fwd_steps, w.sens)
         dom = 2 if w.adjoint else 0
         dom_ms = float(kern_ms[:, dom].mean())
         achieved = bytes_solve * B / (dom_ms * 1e-3) / 1e9
@@ -450,7 +475,8 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
         # which build of the backward kernel did the work (the device-side rule of sb_api.cpp)
         flat = w.adjoint and group == 1 and mean_fwd_steps * (1 - n_fail / max(B, 1)) > FLAT_FWD_STEPS_PER_TVAL * n_t
         kernel = ('sb_backward_fund' if BACKWARD == 'fundamental' else
-                  'sb_backward_flat' if flat else 'sb_backward') if w.adjoint else 'sb_forward'
+                  'sb_backward_flat' if flat else 'sb_backward') if w.adjoint else (
+                      'sb_forward_sens' if w.sens else 'sb_forward')
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         if os.path.exists(tpath):

@@ -83,6 +83,7 @@ class Workload:
     adjoint: bool
     history_capacity: int
     cotangent: str = 'ones'
+    sens: bool = False          # forward sensitivities dy/dp (Solver(sens_mode=...)) instead of the adjoint
 
     def grads(self, n_states: int) -> np.ndarray:
         """Cotangent ``g[n_t, n_s]`` shared by all instances: all ones as in the reference's
@@ -112,6 +113,9 @@ def workloads() -> Dict[str, Workload]:
     return {
         'lv_fwd': Workload('lv_fwd', lotka_volterra, (0.1, 0.2, 0.3, 0.4), 0.25, (1.0, 0.1), 0.0,
                            lv_t, 65536, 20261017 + 2, False, 512),
+        # forward sensitivity analysis of the same problem (dy/dalpha, dy/dbeta)
+        'lv_fsa': Workload('lv_fsa', lotka_volterra, (0.1, 0.2, 0.3, 0.4), 0.25, (1.0, 0.1), 0.0,
+                           lv_t, 65536, 20261017 + 2, False, 512, sens=True),
         'lv_adj': Workload('lv_adj', lotka_volterra, (0.1, 0.2, 0.3, 0.4), 0.25, (1.0, 0.1), 0.0,
                            lv_t, 65536, 20261017 + 2, True, 512),
         'robertson_adj': Workload('robertson_adj', robertson, (0.04, 3e7, 1e4), 0.1,
