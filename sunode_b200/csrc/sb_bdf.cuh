@@ -862,7 +862,79 @@ struct Bdf {
     }
 
     // ------------------------------------------------------------------ cvSetBDF + cvSetTqBDF
+    // Same quantities, same operands per operation as CVODES' cvSetBDF / cvSetTqBDF, arranged for
+    // the FP64 pipe: a division is a chain of eight dependent operations and this routine makes
+    // up to fourteen, so (i) every ratio h / (h + tau_1 + ... + tau_{j-1}) the routine can need is
+    // formed up front -- five independent chains that overlap -- and picked by order afterwards,
+    // (ii) the order / qwait cases are selects instead of branches, which lets the remaining
+    // independent divisions (tq[2], tq[5], C, C', C'', 1/l1) overlap as well.  Values that a case
+    // does not use may be inf / NaN (zero denominators at order 1); they are never selected.
     __device__ __forceinline__ void set_coeffs() {
+#ifdef SB_COEFFS_BRANCHY
+        set_coeffs_branchy();
+#else
+        // x[j] = h / hs_j,  hs_j = h + tau[1] + ... + tau[j-1]   (j = 2 .. 6)
+        double hs = h, x[SB_LMAX + 1];
+#pragma unroll
+        for (int j = 2; j <= SB_LMAX; ++j) { hs += tau[j - 1]; x[j] = sb_div(h, hs); }
+        // xi_inv of the alpha0_hat term: x[q] (order > 1); of the tq[3] term: x[q + 1]
+        double xq = 1.0, xq1 = 1.0, lq = 1.0, alpha0 = -1.0;
+        static_for<1, SB_LMAX>([&](auto J_) {
+            constexpr int j = SB_IDX(J_);
+            if (j >= 2) xq = (j == q) ? x[j] : xq;
+            xq1 = (j == q) ? x[j + 1] : xq1;
+        });
+#pragma unroll
+        for (int i = 0; i < SB_LMAX; ++i) l[i] = 0.0;
+        l[0] = l[1] = 1.0;
+#pragma unroll
+        for (int j = 2; j < SB_QMAX; ++j) {
+            const bool on = j < q;
+            alpha0 = on ? alpha0 - 1.0 / (double)j : alpha0;
+#pragma unroll
+            for (int i = SB_QMAX; i >= 1; --i)
+                if (i <= j) l[i] = on ? fma(l[i - 1], x[j], l[i]) : l[i];
+        }
+        const bool hi = q > 1;
+        alpha0 = hi ? alpha0 - sb_rk_table[q] : alpha0;
+        const double xistar_inv = hi ? -l[1] - alpha0 : 1.0;
+        const double xi_inv = hi ? xq : 1.0;
+        const double alpha0_hat = hi ? -l[1] - xi_inv : -1.0;
+#pragma unroll
+        for (int i = SB_QMAX; i >= 1; --i) l[i] = (hi && i <= q) ? fma(l[i - 1], xistar_inv, l[i]) : l[i];
+        static_for<1, SB_LMAX>([&](auto J_) {
+            constexpr int j = SB_IDX(J_);
+            lq = (j == q) ? l[j] : lq;
+        });
+        const double A1 = 1.0 - alpha0_hat + alpha0;
+        const double A2 = 1.0 + q * A1;
+        const double tq2 = sb_div(A1, alpha0 * A2);
+        const double tq5 = fabs(sb_div(A2 * xistar_inv, lq * xi_inv));
+        // the qwait == 1 quantities (used by the order selection of this step)
+        const double C = sb_div(xistar_inv, lq);
+        const double A3 = alpha0 + sb_rk_table[q];
+        const double A4 = alpha0_hat + xi_inv;
+        const double Cpinv = sb_div(1.0 - A4 + A3, A3);
+        const double A5 = alpha0 - sb_rk_table[q + 1];
+        const double A6 = alpha0_hat - xq1;
+        const double Cppinv = sb_div(1.0 - A6 + A5, A2);
+        const double tq3 = sb_div(Cppinv, xq1 * (q + 2) * A5);
+        const double rl = sb_div(1.0, l[1]);
+        tq[2] = tq2 * tq2;
+        tq[5] = tq5;
+        if (qwait == 1) {
+            tq[1] = hi ? (C * Cpinv) * (C * Cpinv) : 1.0;
+            tq[3] = tq3 * tq3;
+        }
+        tq[4] = tq[2] * (1.0 / (NLSCOEF * NLSCOEF));   // (tq[2] / nlscoef)^2 = 1 / CVODES' tq[4]^2, a factor
+        rl1 = rl;
+        gamma = h * rl1;
+        if (nst == 0) gammap = gamma;
+        gamrat = (nst > 0) ? sb_div(gamma, gammap) : 1.0;
+#endif
+    }
+
+    __device__ __forceinline__ void set_coeffs_branchy() {
         double xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0, hsum = h;
 #pragma unroll
         for (int i = 0; i < SB_LMAX; ++i) l[i] = 0.0;
