@@ -198,6 +198,42 @@ SB_ROOT_FN double eta_root2(double x2, int k) {
 #endif
 }
 
+// Three roots at once (the order selection's eta_q, eta_{q-1}, eta_{q+1}): the same sequence as
+// eta_root2 per root, written side by side so that the three dependent chains (~25 operations
+// each) overlap in the FP64 pipe instead of running one after the other.  Bit-identical to three
+// calls of eta_root2.
+__device__ __forceinline__ void eta_root2x3(const double* x2, const int* k, double* out) {
+#if defined(SB_EXACT_ROOT) || defined(SB_ETA_SERIAL)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = eta_root2(x2[i], k[i]);
+#else
+    bool regular = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) regular = regular && (x2[i] > 1e-36 && x2[i] < 1e36);
+    if (!regular) {                                                  // 0, inf, nan, extreme: rare
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = eta_root2(x2[i], k[i]);
+        return;
+    }
+    double a[3], z0[3], r[3], z[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        a[i] = 0.5 * sb_rk_table[k[i]];
+#ifdef SB_HOST_EMULATION
+        z0[i] = (double)powf((float)x2[i], -0.5f / (float)k[i]);
+#else
+        z0[i] = (double)exp2f(-__log2f((float)x2[i]) * (float)a[i]);
+#endif
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r[i] = fma(x2[i], sb_ipow(z0[i] * z0[i], k[i]), -1.0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) z[i] = z0[i] * fma(r[i] * a[i], fma(0.5 * (1.0 + a[i]), r[i], -1.0), 1.0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = sb_div(z[i], fma(ADDON, z[i], 1.0));
+#endif
+}
+
 template <int N>
 __device__ __forceinline__ bool all_finite(const double* v) {
     double s = 0.0;
@@ -1158,11 +1194,15 @@ struct Bdf {
             qprime = q; hprime = h; eta = 1.0;
             return;
         }
-        const double etaq = eta_root2((BIAS2 * BIAS2) * dsm2, L);
-        if (qwait != 0) { eta = etaq; qprime = q; set_eta(); return; }
-        qwait = 2;
-        double etaqm1 = 0.0, etaqp1 = 0.0;
-        if (q > 1) {
+        // the lanes of a warp that select the order in this step first form the two extra error
+        // norms; then ALL lanes take the three roots together (lanes that need only eta_q pass
+        // dummies): one call site, three overlapping chains
+        const bool select = qwait == 0;
+        const bool need_m1 = select && q > 1;
+        const bool need_p1 = select && q != SB_QMAX && saved_tq5 != 0.0;
+        double x2[3] = {(BIAS2 * BIAS2) * dsm2, 1.0, 1.0}, etas[3];
+        int ks[3] = {L, 1, 1};
+        if (need_m1) {
             double zq[N], zqQ[NQ_];
 #pragma unroll
             for (int i = 0; i < N; ++i) zq[i] = 0.0;
@@ -1179,9 +1219,9 @@ struct Bdf {
             double ddn2 = norm2(zq);
             if (QUAD) ddn2 = fmax(ddn2, ms_q(zqQ));
             ddn2 *= tq[1];
-            etaqm1 = eta_root2((BIAS1 * BIAS1) * ddn2, q);
+            x2[1] = (BIAS1 * BIAS1) * ddn2; ks[1] = q;
         }
-        if (q != SB_QMAX && saved_tq5 != 0.0) {
+        if (need_p1) {
             const double r = sb_div(h, tau[2]);
             double rp = r;
 #pragma unroll
@@ -1198,8 +1238,13 @@ struct Bdf {
                 dup2 = fmax(dup2, ms_q(tmpq));
             }
             dup2 *= tq[3];
-            etaqp1 = eta_root2((BIAS3 * BIAS3) * dup2, L + 1);
+            x2[2] = (BIAS3 * BIAS3) * dup2; ks[2] = L + 1;
         }
+        eta_root2x3(x2, ks, etas);
+        const double etaq = etas[0];
+        if (!select) { eta = etaq; qprime = q; set_eta(); return; }
+        qwait = 2;
+        const double etaqm1 = need_m1 ? etas[1] : 0.0, etaqp1 = need_p1 ? etas[2] : 0.0;
         const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
         if (etam < THRESH) { eta = 1.0; qprime = q; }
         else if (etam == etaq) { eta = etaq; qprime = q; }
