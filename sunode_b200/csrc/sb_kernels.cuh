@@ -370,6 +370,27 @@ struct BwdSys {
             bool went_left = false;
 #pragma unroll 1
             for (;;) {
+#if !defined(SB_HOST_EMULATION) && !defined(SB_TAB_LOAD64)
+                // 16-byte loads: the entry (an even number of doubles, 16-byte aligned) comes in
+                // half as many load instructions -- every one of them touches a different cache
+                // line per lane, and waiting for them was the largest single stall of the pass
+                static_assert(TAB_STRIDE % 2 == 0, "entry length");
+                double v[TAB_STRIDE];
+#pragma unroll
+                for (int i = 0; i < TAB_STRIDE / 2; ++i) {
+                    const double2 d = __ldg(reinterpret_cast<const double2*>(e) + i);
+                    v[2 * i] = d.x; v[2 * i + 1] = d.y;
+                }
+                lo = v[0]; hi = v[1];
+                order = (int)v[2];
+                inv_delt = v[3];
+#pragma unroll
+                for (int i = 0; i < SB_QMAX; ++i) T[i] = v[4 + i];
+#pragma unroll
+                for (int j = 0; j < SB_LMAX; ++j)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) Y[j][k] = v[10 + NS * j + k];
+#else
                 lo = __ldg(e); hi = __ldg(e + 1);
                 order = (int)__ldg(e + 2);
                 inv_delt = __ldg(e + 3);
@@ -379,6 +400,7 @@ struct BwdSys {
                 for (int j = 0; j < SB_LMAX; ++j)
 #pragma unroll
                     for (int k = 0; k < NS; ++k) Y[j][k] = __ldg(e + 10 + NS * j + k);
+#endif
                 // CVAfindIndex: keep the interval while t_lo <= t <= t_hi, else walk
                 if ((t < lo || (went_left && t <= lo)) && idx > 1) { --idx; e -= TAB_STRIDE; went_left = true; }
                 else if (t > hi && idx < np - 1 && !went_left) { ++idx; e += TAB_STRIDE; }
