@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 O, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
 
-for f in ('bench_lv_adj', 'bench_lv_fwd', 'bench_robertson_adj', 'bench_seir_adj_32768', 'bench_lv_adj_reference_arm'):
+for f in ('bench_default', 'bench_lv_adj', 'bench_lv_fwd', 'bench_robertson_adj', 'bench_seir_adj_32768',
+          'bench_lv_adj_reference_arm'):
     if os.path.exists('%s/%s.json' % (O, f)):
         shutil.copy('%s/%s.json' % (O, f), '%s/%s_%s.json' % (P, tag, f))
 
@@ -44,7 +45,10 @@ def dram(rep):
 
 
 reps = {'lv_adj:65536:sb_backward': 'ncu_sb_backward_lv', 'lv_fwd:65536:sb_forward': 'ncu_sb_forward_lv',
-        'seir_adj:32768:sb_backward': 'ncu_sb_backward_seir', 'robertson_adj:16384:sb_backward': 'ncu_sb_backward_flat_robertson'}
+        'seir_adj:32768:sb_backward': 'ncu_sb_backward_seir',
+        'robertson_adj:16384:sb_backward_flat': 'ncu_sb_backward_flat_robertson',
+        'lv_adj:65536:sb_backward_fund': 'ncu_sb_backward_fund_lv', 'lv_adj:65536:sb_tables': 'ncu_sb_tables_lv',
+        'seir_adj:32768:sb_forward': 'ncu_sb_forward_seir'}
 t = {'_comment': 'dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an `ncu --set full` capture '
                  '(profiles/%s_ncu_*.txt; caches flushed before every replay pass, dirty lines still in L2 at the end '
                  'of the launch are not counted), keyed by workload:batch:kernel; bench.py copies the matching entry '
