@@ -298,6 +298,11 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
     gather = world > 1 and not args.no_gather
     counts = [B] * world
     if gather:
+        if w.adjoint:
+            # the forward kernel writes into symmetric memory, peers pull it with their copy engines
+            sym, _ = sharding.symmetric_rows((B, n_t, n_s), dev)
+            if sym is not None:
+                y_d = sym
         y_all = torch.empty((world * B, n_t, n_s), dtype=torch.float64, device=dev)
         small_all = torch.empty((world * B, n_d + n_s + 1), dtype=torch.float64, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -513,7 +518,9 @@ def measure(args, name, *, steps, warmup, backward, batch, rank, world, local_ra
                 'l2': 'L2 flushed between timed iterations (512 MiB memset, untimed)',
                 'failed_instances': n_fail, 'failed_status_rank0': fail_codes,
                 'collective': ('all_gather(y_out) issued after the forward kernel, in flight under the '
-                               'backward kernels, + all_gather(grad|lamda0|status) per step'
+                               'backward kernels (%s), + NCCL all_gather(grad|lamda0|status) per step'
+                               % ('peer-to-peer pulls from symmetric memory by the copy engines'
+                                  if sharding.last_transport() == 'p2p' else 'NCCL')
                                if gather and w.adjoint else 'all_gather(y_out) per step' if gather else 'none')}),
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
             'setup': setup,
