@@ -513,7 +513,15 @@ class AdjointSolver(_ParamsMixin):
     def solve_forward_batch(self, t0, tvals, y0, params=None, y_out=None, *, status=None,
                             stats=None, max_retries=5, stream=None):
         """Batched ``solve_forward``; the step history of every instance stays on the device
-        for a following :meth:`solve_backward_batch`."""
+        for a following :meth:`solve_backward_batch`.
+
+        History capacity: with host (numpy) arrays and no explicit ``history_capacity`` the store
+        grows like the reference's checkpoints do -- instances that ran out of slots
+        (``CV_TOO_MUCH_WORK`` with every slot used) make the solve repeat with four times the
+        capacity, up to ``checkpoint_n``.  With device (torch CUDA) arrays the call is asynchronous
+        and the status is not inspected: the capacity is what the solver was created with (default
+        1 024 steps), such instances report ``CV_TOO_MUCH_WORK``; pass ``history_capacity=`` for
+        problems that take more forward steps."""
         y0 = self._flat_state(y0)
         B = int(y0.shape[0])
         tvals = np.asarray(tvals, dtype=np.float64)

@@ -355,3 +355,33 @@ def test_ten_state_chain_grouped_lanes_with_padding():
     assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1e-2
     np.testing.assert_allclose(grad, go, rtol=1e-7)
     np.testing.assert_allclose(lam, lo, rtol=1e-7, atol=1e-12)
+
+
+def test_chunked_adjoint_equals_single_launch():
+    """Bounded memory (`AdjointSolver.set_workspace_limit`, the counterpart of the reference's
+    `checkpoint_n`, solver.py:533,588): a workspace limit below the batch's history + tables cuts
+    `sb_solve_adjoint` into chunks; host arrays and device tensors, results bit for bit those of
+    the single launch."""
+    torch = pytest.importorskip('torch')
+    w = examples.workloads()['lv_adj']
+    prob = w.make_problem()
+    B = 5000
+    y0, theta = w.draws(B)
+    grads = np.random.default_rng(11).standard_normal((B, len(w.tvals), prob.n_states))
+    one = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    ref = one.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert one._engine.last_chunks() == 1 and (ref[3] == 0).all()
+    per_instance = 512 * ((2 + 2) + (10 + 6 * 2)) * 8
+    cut = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512)
+    cut.set_workspace_limit(2048 * per_instance + 1)
+    out = cut.solve_adjoint_batch(w.t0, w.tvals, y0, theta, grads)
+    assert cut._engine.last_chunks() == 3                      # 2048 + 2048 + 904
+    for a, b in zip(ref, out):
+        np.testing.assert_array_equal(a, b)
+    dev = torch.device('cuda', 0)
+    td = [torch.from_numpy(a).to(dev) for a in (y0, theta, grads)]
+    yd, gd, ld, sd = cut.solve_adjoint_batch(w.t0, w.tvals, *td)
+    torch.cuda.synchronize()
+    assert cut._engine.last_chunks() == 3
+    for a, b in zip(ref, (yd, gd, ld, sd)):
+        np.testing.assert_array_equal(a, b.cpu().numpy())
