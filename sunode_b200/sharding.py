@@ -187,13 +187,14 @@ def solve_adjoint_gathered(solver: Any, t0: float, tvals, y0, params, grads, cou
         if (transport in (None, 'p2p') and not as_numpy and y0.is_cuda and len(set(counts)) == 1
                 and hasattr(solver, '_problem')):
             shape = (int(y0.shape[0]), len(tvals), solver._problem.n_states)
-            if y_out is not None and tuple(y_out.shape) == shape:
+            if y_out is not None:
+                # a caller-supplied output buffer is used as it is: peer pulls only if it IS a
+                # symmetric buffer (symmetric_rows), else the NCCL transport
                 handle = next((h for t, h in _symm.values()
-                               if t is not None and t.data_ptr() == y_out.data_ptr()), None)
-            if handle is None:
-                sym, handle = symmetric_rows(shape, y0.device, group)
-                if handle is not None:
-                    y_out = sym
+                               if t is not None and t.data_ptr() == y_out.data_ptr()
+                               and tuple(t.shape) == tuple(y_out.shape)), None)
+            else:
+                y_out, handle = symmetric_rows(shape, y0.device, group)
         if transport == 'p2p' and handle is None:
             raise RuntimeError('symmetric memory is not available for the p2p transport')
         y, st_f = solver.solve_forward_batch(t0, tvals, y0, params, y_out=y_out)
