@@ -237,28 +237,24 @@ def test_robertson_gradients_against_tight_solve():
 
 def test_g6_sundials_roberts_example_on_the_gpu():
     """SUNDIALS' own dense Robertson example (cvRoberts_dns: rtol 1e-4, per-state atol, t up to
-    4e10; tests/test_oracle.py::test_g6 holds the published statistics) through `sb_forward`:
-    CVODE's work counters to 15 % -- 11 or 12 Jacobian evaluations, no convergence failure -- and
-    the oracle's solution to a few tolerance units in the transient."""
+    4e10; tests/test_oracle.py::test_g6 holds the published statistics and the provenance caveat)
+    through `sb_forward`: batch-mean work counters within 10 % of the published CVODE run and
+    within 3 % of the oracle's on the same 64 draws, no convergence failure, and -- per draw --
+    the oracle's solution to a few tolerance units in the transient (the two step sequences
+    decorrelate on this problem: the step count of ONE draw scatters by +-15 %)."""
     from oracle.oracle import Oracle
+    from tests.test_oracle import check_roberts_dns_counters, roberts_dns_inputs
     prob = examples.robertson()
-    tv = 0.4 * 10.0 ** np.arange(12)
-    atol = np.array([1e-8, 1e-14, 1e-6])
-    y0, th = np.array([[1.0, 0.0, 0.0]]), np.array([[0.04, 3e7, 1e4]])
-    solver = Solver(prob, abstol=atol, reltol=1e-4)
-    stats = np.zeros((1, 8), dtype=np.int32)
-    y, status = solver.solve_batch(0.0, tv, y0, th, stats=stats, max_retries=10)
+    tv, atol, y0, th = roberts_dns_inputs()
+    stats = np.zeros((len(y0), 8), dtype=np.int32)
+    y, status = Solver(prob, abstol=atol, reltol=1e-4).solve_batch(0.0, tv, y0, th, stats=stats,
+                                                                  max_retries=10)
     yo, so, sto = Oracle(prob, rtol=1e-4, atol=atol, mxstep=5000).solve_forward(0.0, tv, y0, th)
-    assert status[0] == 0 and so[0] == 0
-    nst, nfe, nje, nsetups, netf, ncfn, nni = (int(v) for v in stats[0, :7])
-    # the published statistics: nst 542, nfe 754, nsetups 107, nje 11, nni 751, ncfn 0, netf 22.  On
-    # this stiff problem at a loose tolerance the step sequence is sensitive to rounding: the
-    # device arithmetic (561 steps on the emulated code) and the oracle (503) bracket the published
-    # run; each must be within 15 % of it
-    assert abs(nje - 11) <= 2 and ncfn == 0, stats[0]
-    for mine, pub in ((nst, 542), (nfe, 754), (nsetups, 107), (nni, 751)):
-        assert abs(mine - pub) <= 0.15 * pub, (stats[0], sto[0, :7])
-    assert 12 <= netf <= 35, netf
-    units = np.abs(y[0] - yo[0]) / (1e-4 * np.abs(yo[0]) + atol)
-    assert units[:6].max() <= 10.0, units[:6].max()          # transient (observed: 5.7)
-    assert units.max() <= 30.0, units.max()                  # tail (see tests/test_oracle.py::test_g6)
+    assert (status == 0).all() and (so == 0).all()
+    mean = check_roberts_dns_counters(stats)
+    mean_o = sto[:, :7].astype(float).mean(axis=0)
+    for k in (0, 1, 3, 6):
+        assert abs(mean[k] - mean_o[k]) <= 0.03 * mean_o[k], (mean, mean_o)
+    units = np.abs(y - yo) / (1e-4 * np.abs(yo) + atol)
+    assert units[:, :6].max() <= 10.0, units[:, :6].max()    # transient (observed: 5.7)
+    assert units.max() <= 30.0, units.max()                  # tail
