@@ -490,4 +490,260 @@ __device__ __forceinline__ void backward_unit_group(const SbBackwardArgs& a, lon
     }
 }
 
+
+// ------------------------------------------------------------------------------------ forward
+// The forward kernels (sb_forward, sb_forward_sens) in lane groups: the same split of the state
+// over the G lanes of a group as in the backward kernel -- lane r owns the components
+// r*C .. r*C + C - 1 of y (and of every sensitivity block) and the same rows of the saved Jacobian
+// and of I - gamma*J.  Every lane evaluates the whole generated right-hand side on the group's
+// copy of the evaluation vector (shared memory) and keeps its components.
+template <int G, int NBLK>
+struct FwdSysG {
+    using LG = LaneGroup<G>;
+    static constexpr bool TSTOP = false;
+#ifdef SB_CONSTRAINTS
+    static constexpr bool CONSTR = false;          // constraint builds run one lane per instance
+#endif
+    static constexpr int GROUP = G, NS_FULL = NS, NQ_FULL = 1;
+    static constexpr bool MAT_SHARED = true;
+    static constexpr int C = (NS + G - 1) / G;     // state components (and matrix rows) per lane
+    const SbForwardArgs& a;
+    using GroupIds = typename LG::Ids;
+    GroupIds id;
+    __device__ __forceinline__ explicit FwdSysG(const SbForwardArgs& a_) : a(a_), id(LG::ids()) {}
+    __device__ __forceinline__ double rtol() const { return a.rtol; }
+    // i = b*C + c: component c of block b held by this lane (padding rows use the last state's)
+    __device__ __forceinline__ double atol(int i) const {
+        const int b = i / C, c = i - b * C;
+        const int g = id.r * C + c;
+        return __ldg(a.atol + b * NS + (g < NS ? g : NS - 1));
+    }
+    __device__ __forceinline__ double rtolQ() const { return 0.0; }
+    __device__ __forceinline__ double atolQ() const { return 1.0; }
+    __device__ __forceinline__ double tstop() const { return 0.0; }
+    __device__ __forceinline__ static double gsum(double x, GroupIds g) { return LG::sum(x, g.gm); }
+    __device__ __forceinline__ static double gmax(double x, GroupIds g) { return LG::max(x, g.gm); }
+    __device__ __forceinline__ static bool gall(bool b, GroupIds g) { return LG::all(b, g.gm); }
+    static constexpr int ROW = (C * NS + C) | 1;
+    __device__ __forceinline__ void add_identity(double* m) const {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (id.r * C + c < NS) m[c * NS + id.r * C + c] += 1.0;
+    }
+    __device__ __forceinline__ bool lu_factor(double* m, int* piv) const {
+        return LG::template lu_factor<NS, C, 2 * ROW + 1>(m, piv, id);
+    }
+    __device__ __forceinline__ void lu_solve(const double* m, const int* piv, double* b) const {
+        LG::template lu_solve<NS, C>(m, piv, b, id);
+    }
+
+    const double* p;       // this instance's parameters (global memory)
+    double t;
+    double* yv;            // the vector an evaluation is made at, all blocks: the group's [NS * NBLK] slot
+    __device__ __forceinline__ void set_time(double t_) { t = t_; }
+    __device__ __forceinline__ void gather(const double* mine) const {
+        __syncwarp(id.gm);                        // the previous contents have been consumed
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (id.r * C + c < NS) yv[b * NS + id.r * C + c] = mine[b * C + c];
+        __syncwarp(id.gm);
+    }
+    __device__ __forceinline__ void rhs(const double* y_mine, double* out_mine) const {
+        double out[NS];
+        gather(y_mine);
+        sb_rhs(t, yv, p, out);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out_mine[c] = LG::template pick<NS>(out, id.r * C + c);
+        if constexpr (NBLK > 1) {
+            double so[(NBLK - 1) * NS];
+            sb_sens_rhs(t, yv, yv + NS, p, so);
+#pragma unroll
+            for (int b = 1; b < NBLK; ++b)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    out_mine[b * C + c] = LG::template pick<NS>(so + (b - 1) * NS, id.r * C + c);
+        }
+    }
+    __device__ __forceinline__ void jac(const double* y_mine, double* Jrow) const {
+        double J[NS * NS];
+        gather(y_mine);
+        sb_jac(t, yv, p, J);
+        const int r = id.r;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            static_for<0, NS>([&](auto J_) {
+                constexpr int j = SB_IDX(J_);
+                Jrow[c * NS + j] = LG::template pick<NS>(J + NS * j, r * C + c);     // column-major: J[row + NS*j]
+            });
+    }
+    __device__ __forceinline__ void quad(const double*, double*) const {}
+};
+
+// forward_instance_t of sb_kernels.cuh for grouped lanes.  `inst` / `valid` are per group; the
+// output-time loop is flattened into the step loop as there, and all lanes of a group take every
+// branch together (the controller record is the group's, in shared memory).
+template <int G, int NBLK>
+__device__ __forceinline__ void forward_instance_group(const SbForwardArgs& a, long long inst, bool valid) {
+    using Sys = FwdSysG<G, NBLK>;
+    using LG = LaneGroup<G>;
+    constexpr int C = Sys::C;
+    constexpr int NL = C * NBLK;                  // components this lane holds
+    using Integrator = Bdf<C, 0, Sys, NBLK>;
+    if (!valid) inst = 0;
+    Sys sys(a);
+    const int r = sys.id.r;
+    const unsigned gm = sys.id.gm;
+    bool has_y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) has_y[c] = r * C + c < NS;
+    const bool writer = r == 0;
+
+    struct Shared { typename Integrator::Ctl ctl; double yv[NS * NBLK]; };
+    __shared__ Shared sh_all[(SB_BLOCK / 32) * (32 / G)];
+    Shared& sh = sh_all[(threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G)];
+    struct Rows { typename Integrator::Mat mat; double pad; };
+    static_assert(sizeof(Rows) == (2 * Sys::ROW + 1) * sizeof(double), "row stride");
+    __shared__ Rows rows_all[SB_BLOCK];
+#if SB_GROUP_SHARED_CTL
+    Integrator bdf(sh.ctl, rows_all[threadIdx.x].mat);
+#else
+    typename Integrator::Ctl ctl_private;
+    Integrator bdf(ctl_private, rows_all[threadIdx.x].mat);
+#endif
+    bdf.gid = sys.id;
+    sys.yv = sh.yv;
+    sys.p = a.params + inst * NP;
+    sys.t = 0.0;
+
+    double y0[NL];
+#pragma unroll
+    for (int c = 0; c < C; ++c) y0[c] = has_y[c] ? a.y0[inst * NS + r * C + c] : 0.0;
+    if constexpr (NBLK > 1) {
+        const double* s0 = a.sens0_shared ? a.sens0 : a.sens0 + (size_t)inst * (NBLK - 1) * NS;
+#pragma unroll
+        for (int b = 1; b < NBLK; ++b)
+#pragma unroll
+            for (int c = 0; c < C; ++c) y0[b * C + c] = has_y[c] ? s0[(b - 1) * NS + r * C + c] : 0.0;
+    }
+    bool joined = LG::converge(gm);               // (the loads above are lane-dependent)
+    bdf.clear_stats();
+    bdf.reinit(a.t0, y0, nullptr);
+
+    double* yo = a.y_out + (size_t)inst * a.n_t * NS;
+    double* so = (NBLK > 1) ? a.sens_out + (size_t)inst * a.n_t * (NBLK - 1) * NS : nullptr;
+    double* hist = a.hist ? a.hist + (size_t)inst * a.hist_cap * HIST_STRIDE : nullptr;
+    // (t, order, y[, y']) of a stored point: every lane its components, lane 0 the header
+    auto store = [&](int idx, int order) {
+        double* e = hist + (size_t)idx * HIST_STRIDE;
+        if (writer) { e[0] = bdf.tn; e[1] = (double)order; }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (has_y[c]) {
+                e[2 + r * C + c] = bdf.zn[0][c];
+#ifdef SB_HERMITE
+                e[2 + NS + r * C + c] = bdf.zn[1][c] / bdf.h;
+#endif
+            }
+    };
+    auto emit = [&](int k, const double* v) {     // row k of the outputs from this lane's components
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (has_y[c]) {
+                yo[(size_t)k * NS + r * C + c] = v[c];
+                if constexpr (NBLK > 1) {
+#pragma unroll
+                    for (int b = 1; b < NBLK; ++b)
+                        so[((size_t)k * (NBLK - 1) + (b - 1)) * NS + r * C + c] = v[b * C + c];
+                }
+            }
+    };
+    int status = SB_SUCCESS;
+    int k = 0;          // next output time
+    int nloc = 0;       // internal steps taken towards tvals[k]
+
+    for (;;) {
+        joined = LG::converge(gm) && joined;
+        bool work = valid && status == SB_SUCCESS && k < a.n_t;
+        if (work && !bdf.in_step) {
+            for (;;) {
+                const double tout = a.tvals[k];
+                if (tout == a.t0) {
+                    emit(0, y0);                  // the reference writes row 0 here whatever k is
+                } else if (bdf.nst > 0 && (bdf.tn - tout) * bdf.h >= 0.0) {
+                    double yk[NL];
+                    bdf.get_dky(tout, yk);
+                    emit(k, yk);
+                } else {
+                    break;
+                }
+                nloc = 0;
+                if (++k == a.n_t) { work = false; break; }
+            }
+        }
+        joined = LG::converge(gm) && joined;
+        if (work && !bdf.in_step) {
+            if (bdf.nst == 0) {
+                status = bdf.first_call(sys, a.tvals[k]);
+                if (status == SB_SUCCESS && hist) store(0, 0);
+            }
+            if (status == SB_SUCCESS) {
+                if (nloc >= a.max_steps) status = SB_TOO_MUCH_WORK;
+                else if (hist && bdf.nst + 1 >= a.hist_cap) status = SB_TOO_MUCH_WORK;
+                else status = bdf.pre_step_checks(sys);
+            }
+            work = status == SB_SUCCESS;
+        }
+        const unsigned mask = sb_ballot(work);
+        if (mask == 0u) break;
+        joined = LG::together(gm) && joined;
+        joined = LG::converge(gm) && joined;
+        if (work) {
+            const int rr = bdf.attempt(sys, mask);
+            if (rr == SB_SUCCESS) {
+                nloc++;
+                if (hist) store(bdf.nst, bdf.qu);
+            } else if (rr != SB_TRY_AGAIN) {
+                status = rr;
+            }
+        }
+    }
+    joined = LG::converge(gm) && joined;
+    if (!joined && status == SB_SUCCESS) status = SB_GROUP_SPLIT;    // SB_GROUP_CHECK builds only
+    const int nst_total = bdf.nst;
+    if (a.steps_total) {
+#ifndef SB_HOST_EMULATION
+        unsigned n = (valid && writer && status == SB_SUCCESS) ? (unsigned)nst_total : 0u;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(a.steps_total, (unsigned long long)n);
+#else
+        if (writer && status == SB_SUCCESS) *a.steps_total += (unsigned long long)nst_total;
+#endif
+    }
+    if (!valid) return;
+    if (status != SB_SUCCESS) {
+        for (int j = 0; j < a.n_t; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (has_y[c]) {
+                    yo[(size_t)j * NS + r * C + c] = qnan();
+                    if constexpr (NBLK > 1) {
+#pragma unroll
+                        for (int b = 1; b < NBLK; ++b)
+                            so[((size_t)j * (NBLK - 1) + (b - 1)) * NS + r * C + c] = qnan();
+                    }
+                }
+    }
+    if (!writer) return;
+    a.status[inst] = status;
+    if (a.fail_k) a.fail_k[inst] = (status == SB_SUCCESS) ? -1 : min(k, a.n_t - 1);
+    if (a.hist_n) a.hist_n[inst] = (status == SB_SUCCESS) ? nst_total + 1 : 0;
+    if (a.stats) {
+        int* s = a.stats + inst * SB_STATS_STRIDE;
+        s[0] = bdf.st.nst; s[1] = bdf.st.nfe; s[2] = bdf.st.nje; s[3] = bdf.st.nsetups;
+        s[4] = bdf.st.netf; s[5] = bdf.st.ncfn; s[6] = bdf.st.nni; s[7] = nst_total + 1;
+    }
+}
+
 }  // namespace sb

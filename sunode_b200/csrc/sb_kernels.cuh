@@ -44,6 +44,24 @@ constexpr int GROUP = 1;
 #else
 constexpr int GROUP = SB_GROUP_SIZE(SB_NS);
 #endif
+// Lanes per instance of the forward kernels.  Forward sensitivities (sb_forward_sens: y and ND
+// sensitivity blocks, 56 components for the SEIR problem) run in the backward kernels' lane groups
+// (measured, SEIR, 32 768 draws: 88.5 ms against 98.1 ms with one lane per instance and 9 kB of
+// spills; -DSB_NO_FWD_GROUP restores that).  The plain forward kernel stays one lane per instance:
+// its 8-component state spills 1.5 kB but is still faster (4.2 ms against 6.1 ms in groups, where
+// the scalar controller code runs once per group of lanes instead of once per 32 instances);
+// -DSB_FWD_GROUP builds it in groups.  Constraint builds (cvCheckConstraints is written for one
+// lane per instance) never group.
+#if defined(SB_FWD_GROUP) && !defined(SB_CONSTRAINTS)
+constexpr int FWD_GROUP = GROUP;
+#else
+constexpr int FWD_GROUP = 1;
+#endif
+#if defined(SB_NO_FWD_GROUP) || defined(SB_CONSTRAINTS)
+constexpr int SENS_GROUP = 1;
+#else
+constexpr int SENS_GROUP = GROUP;
+#endif
 constexpr int HIST_STRIDE = SB_HIST_STRIDE(SB_NS);
 constexpr int TAB_STRIDE = SB_TAB_STRIDE(SB_NS);
 
@@ -782,21 +800,33 @@ __device__ __forceinline__ void eval_instance(const SbEvalArgs& a, long long i) 
 __device__ int sb_group_size = sb::GROUP;
 __device__ int sb_hist_stride = sb::HIST_STRIDE;   // doubles per history point (the launcher sizes the buffer)
 
-extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+__device__ int sb_group_size_fwd = sb::FWD_GROUP;    // lanes per instance of sb_forward
+__device__ int sb_group_size_sens = sb::SENS_GROUP;  // ... of sb_forward_sens
+
+// a.lanes instances per warp: one per lane, or one per group of sb::FWD_GROUP lanes
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, sb::FWD_GROUP > 1 ? SB_GROUP_MIN_BLOCKS : SB_MIN_BLOCKS)
 sb_forward(const __grid_constant__ SbForwardArgs a) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long inst = warp * a.lanes + lane;
-    sb::forward_instance(a, inst, lane < a.lanes && inst < a.B);
+    const int slot = lane / sb::FWD_GROUP;
+    const long long inst = warp * a.lanes + slot;
+    if constexpr (sb::FWD_GROUP > 1) sb::forward_instance_group<sb::FWD_GROUP, 1>(a, inst, slot < a.lanes && inst < a.B);
+    else sb::forward_instance(a, inst, slot < a.lanes && inst < a.B);
 }
 
 #if SB_ND > 0
-extern "C" __global__ void __launch_bounds__(SB_BLOCK, SB_MIN_BLOCKS)
+// (y and ND sensitivity blocks per lane: from ten components per lane on, 8 warps per SM with 255
+// registers instead of 12 with 168)
+#define SB_SENS_GROUP_MIN_BLOCKS \
+    ((((SB_NS + sb::SENS_GROUP - 1) / sb::SENS_GROUP) * (1 + SB_ND) >= 10) ? (256 / SB_BLOCK) : SB_GROUP_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(SB_BLOCK, sb::SENS_GROUP > 1 ? SB_SENS_GROUP_MIN_BLOCKS : SB_MIN_BLOCKS)
 sb_forward_sens(const __grid_constant__ SbForwardArgs a) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long inst = warp * a.lanes + lane;
-    sb::forward_sens_instance(a, inst, lane < a.lanes && inst < a.B);
+    const int slot = lane / sb::SENS_GROUP;
+    const long long inst = warp * a.lanes + slot;
+    if constexpr (sb::SENS_GROUP > 1) sb::forward_instance_group<sb::SENS_GROUP, 1 + sb::ND>(a, inst, slot < a.lanes && inst < a.B);
+    else sb::forward_sens_instance(a, inst, slot < a.lanes && inst < a.B);
 }
 #endif
 

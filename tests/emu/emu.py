@@ -89,7 +89,7 @@ class Emulator:
         params = np.ascontiguousarray(np.broadcast_to(params, (B, self.np))) if self.np else np.zeros((B, 1))
         return y0, params, B
 
-    def forward(self, t0, tvals, y0, params, rtol, atol, hist_cap=0, max_steps=2500, tab=None):
+    def forward(self, t0, tvals, y0, params, rtol, atol, hist_cap=0, max_steps=2500, tab=None, group=False):
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)
         y0, params, B = self._prep(y0, params)
         n_t = len(tvals)
@@ -102,11 +102,15 @@ class Emulator:
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         _dp(hist), _ip(hist_n), _ip(status), _ip(stats), B, n_t, hist_cap,
                         max_steps, 0, 32, 0, None, None, _dp(tab), None)
-        self.lib.emu_forward(ctypes.byref(a))
+        if group:
+            assert self.lib.emu_group_size() > 1, 'this problem does not run in lane groups'
+            self.lib.emu_forward_group(ctypes.byref(a))
+        else:
+            self.lib.emu_forward(ctypes.byref(a))
         return dict(y=y_out, status=status, stats=stats, hist=hist, hist_n=hist_n,
                     params=params, tvals=tvals)
 
-    def forward_sens(self, t0, tvals, y0, params, sens0, rtol, atol, max_steps=2500, pbar=None):
+    def forward_sens(self, t0, tvals, y0, params, sens0, rtol, atol, max_steps=2500, pbar=None, group=False):
         tvals = np.ascontiguousarray(tvals, dtype=np.float64)
         y0, params, B = self._prep(y0, params)
         n_t = len(tvals)
@@ -123,7 +127,11 @@ class Emulator:
         a = ForwardArgs(t0, rtol, _dp(tvals), _dp(y0), _dp(params), _dp(atol), _dp(y_out),
                         None, None, _ip(status), _ip(stats), B, n_t, 0, max_steps, shared, 32, 0,
                         _dp(sens0), _dp(sens_out), None, None)
-        self.lib.emu_forward_sens(ctypes.byref(a))
+        if group:
+            assert self.lib.emu_group_size() > 1, 'this problem does not run in lane groups'
+            self.lib.emu_forward_sens_group(ctypes.byref(a))
+        else:
+            self.lib.emu_forward_sens(ctypes.byref(a))
         return dict(y=y_out, sens=sens_out, status=status, stats=stats)
 
     def adjoint(self, t0, tvals, y0, params, grads, rtol, atol, rtol_b=1e-10, atol_b=1e-10,

@@ -13,6 +13,26 @@
 #include "generated_problem.inc"     // generated __device__ functions + SB_NS/SB_NP/SB_ND
 #include "sb_kernels.cuh"
 
+#ifdef SB_HOST_EMULATION_GROUP
+template <int NBLK>
+static void emu_forward_group_t(const SbForwardArgs* a) {
+    constexpr int G = sb::GROUP > 1 ? sb::GROUP : 2;
+    if (sb::GROUP <= 1) return;
+    emu_group.size = G;
+    pthread_barrier_init(&emu_group.bar, nullptr, G);
+    for (long long i = 0; i < a->B; ++i) {
+        std::vector<std::thread> lanes;
+        for (int r = 0; r < G; ++r)
+            lanes.emplace_back([a, i, r]() {
+                threadIdx.x = (unsigned)r; blockDim.x = 32; blockIdx.x = 0;
+                sb::forward_instance_group<G, NBLK>(*a, i, true);
+            });
+        for (auto& t : lanes) t.join();
+    }
+    pthread_barrier_destroy(&emu_group.bar);
+}
+#endif
+
 extern "C" {
 void emu_forward(const SbForwardArgs* a) {
     #pragma omp parallel for schedule(dynamic, 16)
@@ -48,8 +68,12 @@ void emu_backward_unit(const SbBackwardArgs* a, int k0, int k1) {
     for (long long i = 0; i < a->B; ++i) sb::backward_unit<false>(*a, i, true, k0, k1);
 }
 #ifdef SB_HOST_EMULATION_GROUP
-// The grouped-lane backward driver: one group (= one instance) at a time, its lanes as threads.
+// The grouped-lane drivers: one group (= one instance) at a time, its lanes as threads.
 int emu_group_size() { return sb::GROUP; }
+void emu_forward_group(const SbForwardArgs* a) { emu_forward_group_t<1>(a); }
+#if SB_ND > 0
+void emu_forward_sens_group(const SbForwardArgs* a) { emu_forward_group_t<1 + SB_ND>(a); }
+#endif
 void emu_backward_group(const SbBackwardArgs* a) {
     constexpr int G = sb::GROUP > 1 ? sb::GROUP : 2;
     if (sb::GROUP <= 1) return;

@@ -173,6 +173,38 @@ def test_lane_group_code_matches_one_lane_per_instance(tmp_path):
         np.testing.assert_array_equal(one['stats'][:, 7], grp['stats'][:, 7])      # stored points
 
 
+def test_forward_lane_groups_match_one_lane_per_instance(tmp_path):
+    """The grouped forward drivers (csrc/sb_group.cuh: forward_instance_group, plain and with
+    forward sensitivities) on the host, lanes as threads: trajectories, sensitivities and the
+    stored step history of the SEIR problem against the one-lane integrator -- the same step
+    sequence but for rounding-level flips, values to 1e-3 tolerance units."""
+    w = examples.workloads()['seir_adj']
+    prob = w.make_problem()
+    B = 3
+    y0, theta = w.draws(B)
+    for lanes in (None, 8):
+        defines = () if lanes is None else ('SB_GROUP_LANES=%d' % lanes,)
+        emu = Emulator(prob, str(tmp_path), defines=defines, group=True)
+        one = emu.forward(w.t0, w.tvals, y0, theta, 1e-8, 1e-8, hist_cap=512)
+        grp = emu.forward(w.t0, w.tvals, y0, theta, 1e-8, 1e-8, hist_cap=512, group=True)
+        assert (one['status'] == 0).all() and (grp['status'] == 0).all()
+        tol = 1e-8 * np.abs(one['y']) + 1e-8
+        assert np.max(np.abs(grp['y'] - one['y']) / tol) <= 1e-3
+        assert np.max(np.abs(one['stats'][:, 0] - grp['stats'][:, 0]) / one['stats'][:, 0]) <= 0.01
+        np.testing.assert_array_equal(one['hist_n'], grp['hist_n'])
+        for b in range(B):                               # the stored (t, order, y) points
+            n = one['hist_n'][b]
+            np.testing.assert_allclose(grp['hist'][b, :n], one['hist'][b, :n], rtol=1e-9, atol=1e-12)
+    s0 = np.zeros((prob.n_params, prob.n_states))
+    one = emu.forward_sens(w.t0, w.tvals, y0, theta, s0, 1e-6, 1e-6)
+    grp = emu.forward_sens(w.t0, w.tvals, y0, theta, s0, 1e-6, 1e-6, group=True)
+    assert (one['status'] == 0).all() and (grp['status'] == 0).all()
+    assert np.max(np.abs(grp['y'] - one['y']) / (1e-6 * np.abs(one['y']) + 1e-6)) <= 1e-3
+    scale = np.abs(one['sens']).max(axis=(0, 1))
+    assert np.max(np.abs(grp['sens'] - one['sens']) / np.maximum(scale, 1e-300)) <= 1e-7
+    assert np.max(np.abs(one['stats'][:, 0] - grp['stats'][:, 0]) / one['stats'][:, 0]) <= 0.02
+
+
 def test_double_integrator_zero_error_estimates(tmp_path):
     """SURVEY G2 (from_sympy.ipynb cells 39-41) through the device code: the solution is a
     quadratic, the local error estimates are exactly zero from order 2 on, so the step-size ratio

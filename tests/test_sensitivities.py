@@ -114,3 +114,36 @@ def test_gpu_reference_shaped_sensitivity_api():
     out = [[None], [None]]
     ap.SolveODE(solver).perform(None, [np.ones(1), np.array([0.2]), np.zeros(0), np.float64(0.0), t], out)
     np.testing.assert_allclose(out[1][0][1:, 0, 0], (np.exp(t) - 1)[1:], rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_forward_sensitivities_in_lane_groups_match_oracle():
+    """The 8-state SEIR problem: y and the six sensitivity vectors dy/dp_k in lane groups of
+    4 lanes x 2 components per block (csrc/sb_group.cuh, forward_instance_group) against the
+    oracle; and the grouped build against the one-lane-per-instance build of the same kernel."""
+    import os
+    from sunode_b200.solver import Solver
+    w = examples.workloads()['seir_adj']
+    prob = w.make_problem()
+    B = 70                                           # not a multiple of 8 groups per warp
+    y0, theta = w.draws(B)
+    sens0 = np.zeros((prob.n_params, prob.n_states))
+    y, s, st = Solver(prob, abstol=1e-8, reltol=1e-8, sens_mode='simultaneous').solve_sens_batch(
+        w.t0, w.tvals, y0, theta, sens0)
+    yo, so, sto, _ = Oracle(prob, rtol=1e-8, atol=1e-8).solve_forward_sens(w.t0, w.tvals, y0, theta, sens0)
+    assert (st == 0).all() and (sto == 0).all()
+    assert np.max(np.abs(y - yo) / (1e-8 * np.abs(yo) + 1e-8)) <= 1.0
+    assert np.max(np.abs(s - so) / (1e-8 * np.abs(so) + 1e-8)) <= 1.0
+    saved = os.environ.get('SUNODE_B200_DEFINES')
+    os.environ['SUNODE_B200_DEFINES'] = 'SB_NO_FWD_GROUP'
+    try:
+        y1, s1, st1 = Solver(prob, abstol=1e-8, reltol=1e-8, sens_mode='simultaneous').solve_sens_batch(
+            w.t0, w.tvals, y0, theta, sens0)
+    finally:
+        if saved is None:
+            del os.environ['SUNODE_B200_DEFINES']
+        else:
+            os.environ['SUNODE_B200_DEFINES'] = saved
+    assert (st1 == 0).all()
+    assert np.max(np.abs(y - y1) / (1e-8 * np.abs(y1) + 1e-8)) <= 1e-2
+    assert np.max(np.abs(s - s1) / (1e-8 * np.abs(s1) + 1e-8)) <= 1e-2
