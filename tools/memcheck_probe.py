@@ -15,4 +15,9 @@ for name, B in (('lv_adj', 70), ('robertson_adj', 37), ('seir_adj', 21)):
         out = s.solve_adjoint_batch(w.t0, w.tvals, y0, theta, g)
         print(name, 'segments', seg, 'failed', int((out[3] != 0).sum()), 'grad[0]', out[1][0])
     f = Solver(prob, abstol=1e-8, reltol=1e-8, sens_mode='simultaneous')
-    print(name, 'forward sens ok')
+    ys, ss, st = f.solve_sens_batch(w.t0, w.tvals, y0, theta, np.zeros((prob.n_params, prob.n_states)))
+    print(name, 'forward sens: failed', int((st != 0).sum()), 'sens[0, -1, 0]', ss[0, -1, 0])
+    if name == 'lv_adj':
+        os.environ['SUNODE_B200_SEGMENTS'] = '1'
+        fs = AdjointSolver(prob, abstol=1e-8, reltol=1e-8, history_capacity=512, backward='fundamental')
+        print(name, 'restart-free pass: failed', int((fs.solve_adjoint_batch(w.t0, w.tvals, y0, theta, g)[3] != 0).sum()))
