@@ -4,7 +4,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sunode_b200 import examples
 from sunode_b200.solver import AdjointSolver, Solver
+ONLY = os.environ.get('PROBE_ONLY')
 for name, B in (('lv_adj', 70), ('robertson_adj', 37), ('seir_adj', 21)):
+    if ONLY and name != ONLY:
+        continue
     w = examples.workloads()[name]
     prob = w.make_problem()
     y0, theta = w.draws(B)
