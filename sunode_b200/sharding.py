@@ -90,7 +90,8 @@ class _PeerGather:
         self.side.wait_event(ready)
         rank = handle.rank
         with torch.cuda.stream(self.side):
-            handle.barrier()
+            # (bounded: a rank that died must not leave its peers spinning on the device)
+            handle.barrier(timeout_ms=120000)
             for step in range(world):
                 r = (rank - step) % world                       # own block first, then round the ring
                 src = x if r == rank else handle.get_buffer(r, tuple(x.shape), x.dtype)
